@@ -1,0 +1,272 @@
+#!/usr/bin/env python3
+"""bench.py -- decoded-info Gbit/s of the batched NR-LDPC min-sum decoder (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (nr_decode_ldpc semantics, BG1 Zc=384 R=1/3, NMS alpha=0.8,
+exactly 10 flooding iterations, early termination off) over one batch of synthetic codeblocks:
+random bits -> CUDA encoder -> BPSK/AWGN LLRs (Philox, +1 dB), all generated on the device.
+  value  : whole-job Gbit/s of decoded info bits (K = 8448 per codeblock) with the LLRs resident in HBM
+  e2e    : the same metric through the host-buffer C-ABI call (nrldpc_decode_minsum_host): pinned
+           host LLRs in, packed info bits + status + iteration counts out, copies inside the timing
+  roofline / cpu_baseline / clocks : see DESIGN.md "Measurement"
+`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP over all host cores)
+on a bounded sample of the same workload.  The reference itself is pure Python (26 s per codeblock).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BGN, ZC, MAX_ITER, ALPHA, BETA, SNR_DB = 1, 384, 10, 0.8, 0.0, 1.0
+K_INFO, N_CODED = 22 * ZC, 66 * ZC
+ALGO_BYTES_PER_CB = 4 * N_CODED + K_INFO // 8   # fp32 LLRs in + packed info bits out = 102432
+METRIC = "decoded_info_gbit_per_s"
+WORKLOAD = "BG1 Zc=384 R=1/3 NMS(alpha=0.8) min-sum, 10 flooding iterations, no early termination, BPSK/AWGN +1 dB"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, sample_cbs=None, early_term=0):
+    """Time the CPU restatement of the reference (oracle/) with every host thread on a bounded sample."""
+    import numpy as np
+    from oracle import oracle as O
+    O.build()
+    threads = O.num_threads()
+    n = sample_cbs or max(threads * 4, 16)
+    rng = np.random.default_rng(0x5601)
+    ck = rng.integers(0, 2, (n, K_INFO)).astype("i1")
+    dn = O.encode_batch(ck, BGN, ZC)
+    sigma = 10 ** (-SNR_DB / 20)
+    llr = (2 * ((1 - 2 * dn.astype("f8")) + rng.normal(0, sigma, dn.shape)) / sigma ** 2).astype("f4").astype("f8")
+    for _ in range(warmup):
+        O.decode_batch(llr[: max(threads, 1)], ZC, BGN, MAX_ITER, "min-sum", ALPHA, BETA, early_term, np.float64)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.decode_batch(llr, ZC, BGN, MAX_ITER, "min-sum", ALPHA, BETA, early_term, np.float64)
+    dt = time.perf_counter() - t0
+    gbps = steps * n * K_INFO / dt / 1e9
+    return gbps, threads, n, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    gbps, threads, n, sps = cpu_reference_run(steps, warmup)
+    sample = f"{n} codeblocks per step x {steps} steps of the same workload, float64, {threads} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": gbps, "unit": "Gbit/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "codeblocks_per_step": n,
+                   "note": "CPU port of the reference algorithm (oracle/, C + OpenMP); the reference itself is "
+                           "pure Python at ~26 s per codeblock (BASELINE.md) and cannot travel to this box"},
+        "cpu_baseline": {"value": gbps, "unit": "Gbit/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gbps, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from python_5gtoolbox_b200 import engine, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    seed = 0x5601 + rank
+
+    # ---- synthetic workload, generated on the device in slices (encoder + Philox AWGN)
+    llr = torch.empty((B, N_CODED), dtype=torch.float32, device=dev)
+    sent = torch.empty((B, K_INFO), dtype=torch.int8, device=dev)
+    sl = 4096
+    for b0 in range(0, B, sl):
+        nb = min(sl, B - b0)
+        ck = engine.random_bits(nb, K_INFO, seed=seed, device=dev, offset=b0 * (K_INFO // 128 + 1))
+        dn = engine.encode_batch(ck, BGN, ZC)
+        engine.awgn_llr(dn, SNR_DB, seed=seed, offset=b0 * (N_CODED // 4), out=llr[b0:b0 + nb])
+        sent[b0:b0 + nb] = ck
+    info = torch.empty((B, (K_INFO + 31) // 32), dtype=torch.int32, device=dev)
+    status = torch.empty((B,), dtype=torch.uint8, device=dev)
+    iters = torch.empty((B,), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    stream = torch.cuda.current_stream()
+
+    def step():
+        _lib.check(L.nrldpc_decode_minsum(llr.data_ptr(), B, BGN, ZC, MAX_ITER, ALPHA, BETA, 0, None, info.data_ptr(),
+                                          status.data_ptr(), iters.data_ptr(), stream.cuda_stream), "decode")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    cbs_per_s = world * B * args.steps / (ms * 1e-3)
+    value = cbs_per_s * K_INFO / 1e9
+
+    # correctness of what was timed: decoded info bits vs what was sent; counters reduced over ranks
+    got = ((info.view(torch.uint8).unsqueeze(-1) >> torch.arange(8, device=dev, dtype=torch.uint8)) & 1).reshape(B, -1)[:, :K_INFO]
+    blk_err = (got != sent.to(torch.uint8)).any(1)
+    counters = torch.stack([torch.tensor(B, device=dev), blk_err.sum(), (got != sent.to(torch.uint8)).sum(),
+                            iters.sum(), status.sum()]).to(torch.int64)
+    if world > 1:
+        dist.all_reduce(counters)  # the path's only collective: 5 int64 counters
+    cnt = counters.tolist()
+
+    # ---- e2e through the host-buffer C-ABI entry point, pinned host memory
+    Be = min(args.e2e_batch, B)
+    h_llr = torch.empty((Be, N_CODED), dtype=torch.float32).pin_memory()
+    h_llr.copy_(llr[:Be])
+    h_info = torch.empty((Be, (K_INFO + 31) // 32), dtype=torch.int32).pin_memory()
+    h_st = torch.empty((Be,), dtype=torch.uint8).pin_memory()
+    h_it = torch.empty((Be,), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        _lib.check(L.nrldpc_decode_minsum_host(h_llr.data_ptr(), Be, BGN, ZC, MAX_ITER, ALPHA, BETA, 0, None,
+                                               h_info.data_ptr(), h_st.data_ptr(), h_it.data_ptr()), "decode_host")
+
+    e2e_step()
+    barrier()
+    e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        e2e_step()
+    barrier()
+    e_dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
+    e2e_val = world * Be * e_steps * K_INFO / float(e_dt.item()) / 1e9
+    assert torch.equal(h_info.to(dev), info[:Be]), "host path and device path disagree"
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        per_gpu_cbs = cbs_per_s / world
+        achieved = per_gpu_cbs * ALGO_BYTES_PER_CB / 1e9
+        G, nt, smem = (ctypes_int() for _ in range(3))
+        L.nrldpc_decode_minsum_geometry(BGN, ZC, G, nt, smem)
+        out = {
+            "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "codeblocks_per_gpu_per_step": B, "info_bits_per_codeblock": K_INFO,
+                       "l2_policy": f"inputs larger than L2 ({B * N_CODED * 4 / 2**30:.1f} GiB of LLRs per step)",
+                       "kernel_geometry": {"codeblocks_per_cta": G.value, "threads": nt.value, "smem_bytes": smem.value},
+                       "block_error_rate": cnt[1] / cnt[0], "mean_iters": cnt[3] / cnt[0], "parity_ok_frac": cnt[4] / cnt[0]},
+            "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": Be * N_CODED * 4,
+                    "d2h_bytes_per_step": Be * ((K_INFO + 31) // 32 * 4 + 1 + 4), "codeblocks_per_step": Be},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_CB,
+                         "kernel": "decode_minsum_kernel", "kernel_ms": ms / args.steps,
+                         "note": "HBM is not the binding roof of this kernel (10 on-chip iterations per byte); "
+                                 "see DESIGN.md for the issue-slot / shared-memory roof"},
+            "clocks": clk.summary(),
+        }
+        if not args.no_cpu:
+            gbps, threads, n, sps = cpu_reference_run(1, 0)
+            out["cpu_baseline"] = {"value": gbps, "unit": "Gbit/s", "cores": threads, "kind": "port",
+                                   "sample": f"{n} codeblocks of the same workload, float64 C port of the reference (oracle/), "
+                                             f"{threads} OpenMP threads, {sps:.2f} s"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ctypes_int():
+    import ctypes
+    return ctypes.c_int()
+
+
+# dram bytes (read+write) per decode launch from the committed `ncu --set full` capture, or None
+TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 16, help="codeblocks per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 13)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+/*
+ * nrldpc_b200.h -- C ABI of libnrldpc_b200.so: batched 5G NR LDPC (TS 38.212 5.3.2) on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the LDPC hot path of xu753x/python_5gtoolbox.  The reference has
+ * no FFI (it is pure Python); each entry point below names the reference function it replaces
+ * (file:line under the reference root).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; every function returns 0 on success, a negative
+ *     NRLDPC_E* code on failure (never throws); nrldpc_last_error() gives the text for this thread.
+ *   - `_host` functions take HOST buffers and are synchronous (H2D, kernels, D2H inside).
+ *   - the others take DEVICE buffers plus a cudaStream_t passed as void* (NULL = default stream) and
+ *     are asynchronous on that stream; the caller owns every buffer.
+ *   - batches are row-major [B, len]; one (bgn, Zc) per call (a transport block has one Zc,
+ *     py5gphy/ldpc/ldpc_info.py:62-69; mixed-Zc workloads issue one call per group/stream).
+ *   - bit arrays are one int8 per bit (the reference's dtype) unless the name says `packed`.
+ *   - there is no CPU fallback anywhere: without a CUDA device every compute entry point fails.
+ */
+#ifndef NRLDPC_B200_H
+#define NRLDPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRLDPC_OK 0
+#define NRLDPC_EINVAL (-1)  /* bad argument (the reference would raise AssertionError) */
+#define NRLDPC_ECUDA (-2)   /* CUDA runtime error, see nrldpc_last_error() */
+#define NRLDPC_ENOMEM (-3)
+#define NRLDPC_ENODEV (-4)  /* no CUDA device */
+
+/* algo ids for the soft decoders */
+#define NRLDPC_ALGO_MINSUM 0 /* 'min-sum' family: alpha=1,beta=0 plain; alpha<1 NMS; beta>0 OMS; both mixed */
+#define NRLDPC_ALGO_BP 1     /* 'BP' (sum-product) -- generic kernels only */
+
+int nrldpc_version(void);
+const char *nrldpc_last_error(void);
+int nrldpc_device_count(void);
+
+/* ldpc_info.find_iLS (py5gphy/ldpc/ldpc_info.py:81-97): set index 0..7, or 255 for an invalid Zc. */
+int nrldpc_find_ils(int Zc);
+
+/* K, N, N' = N + 2Zc and M for (bgn, Zc) (py5gphy/ldpc/nr_ldpc_decode.py:26-31); any pointer may be NULL. */
+int nrldpc_dims(int bgn, int Zc, int *K, int *N, int *Nfull, int *M);
+
+/*
+ * ldpc_info.getH in sparse form (py5gphy/ldpc/ldpc_info.py:99-139): CSR of the lifted parity-check
+ * matrix, rows and columns ascending.  Host buffers: rowptr[M+1], colidx[nnz*Zc].  Returns #edges.
+ */
+int nrldpc_build_csr(int bgn, int Zc, int32_t *rowptr, int32_t *colidx);
+
+/* ------------------------------------------------------------------ encoder */
+/*
+ * nr_ldpc_encode.encode_ldpc(ck, bgn) for B codeblocks (py5gphy/ldpc/nr_ldpc_encode.py:8-115).
+ *   ck [B,K] int8 in {0,1,-1}; -1 = filler.  If fix_fillers != 0 the fillers at k >= 2Zc are
+ *      overwritten with 0 in place, which is the reference's side effect (:32-35).
+ *   dn [B,N] int8 in {0,1,-1}; -1 at the filler positions (:31-37).
+ */
+int nrldpc_encode(int8_t *d_ck, int B, int bgn, int Zc, int fix_fillers, int8_t *d_dn, void *stream);
+int nrldpc_encode_host(int8_t *ck, int B, int bgn, int Zc, int fix_fillers, int8_t *dn);
+
+/* ------------------------------------------------------------------ min-sum decoder (hot path) */
+/*
+ * nr_ldpc_decode.nr_decode_ldpc(LLRin, Zc, bgn, L, 'min-sum', alpha, beta) for B codeblocks
+ * (py5gphy/ldpc/nr_ldpc_decode.py:11-49 -> decode_ldpc :51-143 -> _min_sum_process :178-227):
+ * flooding schedule, fp32 arithmetic in the reference's operation order, LLR > 0 <=> bit 0,
+ * the 2Zc punctured columns start at LLR 0.
+ *   llr         [B,N] float32 channel LLRs
+ *   max_iter    L
+ *   early_term  1 = reference semantics (syndrome check before every iteration, :107-114);
+ *               0 = always run exactly max_iter iterations (throughput mode, not in the reference)
+ *   ck          [B,N'] int8 hard decisions, or NULL            (blkandcrc = ck[:, 0:K], :47)
+ *   info_packed [B, ceil(K/32)] uint32, bit k of the codeblock at word k/32 bit k%32, or NULL
+ *   status      [B] uint8 1 = all parity checks satisfied (:114,:140-143), or NULL
+ *   iters       [B] int32 number of check-node passes executed, or NULL
+ */
+int nrldpc_decode_minsum(const float *d_llr, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
+                         int early_term, int8_t *d_ck, uint32_t *d_info_packed, uint8_t *d_status,
+                         int32_t *d_iters, void *stream);
+int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
+                              int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters);
+
+/* Launch geometry the hot kernel uses for (bgn, Zc): codeblocks per CTA, threads, dynamic smem bytes. */
+int nrldpc_decode_minsum_geometry(int bgn, int Zc, int *cbs_per_cta, int *threads, int *smem_bytes);
+
+/* ------------------------------------------------------------------ generic-H decoders */
+/*
+ * nr_ldpc_decode.decode_ldpc(LLRin, H, L, algo, alpha, beta) for an arbitrary parity-check matrix
+ * given as CSR (py5gphy/ldpc/nr_ldpc_decode.py:51-143), B codeblocks, same H.
+ *   llr [B,Nv] (fp32 if is_f64 == 0, else fp64 -- the fp64 mode reproduces the reference's
+ *   float64 arithmetic bit for bit for algo = min-sum), ck [B,Nv] int8.
+ *   Host variant only: it owns the temporary device workspace.
+ */
+int nrldpc_decode_csr_host(const void *llr, int is_f64, int B, int M, int Nv, const int32_t *rowptr,
+                           const int32_t *colidx, int max_iter, int algo, double alpha, double beta,
+                           int early_term, int8_t *ck, uint8_t *status, int32_t *iters);
+
+/* The same kernels on the 5G matrix of (bgn, Zc): llr [B,N], 2Zc zeros prepended (:43), ck [B,N']. */
+int nrldpc_decode_soft_ref_host(const void *llr, int is_f64, int B, int bgn, int Zc, int max_iter, int algo,
+                                double alpha, double beta, int early_term, int8_t *ck, uint8_t *status,
+                                int32_t *iters);
+
+/*
+ * ldpc_decoder_bit_flipping.ldpc_decoder_BF(LLRin, H, L) on a CSR H
+ * (py5gphy/ldpc/ldpc_decoder_bit_flipping.py:5-73).  llr [B,Nv] float64 (only its sign is used),
+ * ck [B,Nv] int8 0/1.
+ */
+int nrldpc_decode_bf_csr_host(const double *llr, int B, int M, int Nv, const int32_t *rowptr,
+                              const int32_t *colidx, int max_iter, int8_t *ck, uint8_t *status, int32_t *iters);
+/* nr_decode_ldpc(..., algo='BF') (py5gphy/ldpc/nr_ldpc_decode.py:43,65-67): llr [B,N], ck [B,N']. */
+int nrldpc_decode_bf_host(const double *llr, int B, int bgn, int Zc, int max_iter, int8_t *ck, uint8_t *status,
+                          int32_t *iters);
+
+/* ------------------------------------------------------------------ Monte-Carlo helpers (device) */
+/*
+ * BPSK + AWGN + LLR of nr_ldpc_decode.for_test_5g_ldpc_encoder (py5gphy/ldpc/nr_ldpc_decode.py:252-257)
+ * with a counter-based Philox4x32-10 generator instead of NumPy's global RNG:
+ *   llr = 2 * ((1 - 2 dn) + sigma * n) / sigma^2,  sigma = 10^(-snr_db/20),  n ~ N(0,1).
+ *   dn [B,N] int8 (a -1 filler is sent as LLR 0), llr [B,N] float32.
+ */
+int nrldpc_awgn_llr(const int8_t *d_dn, long long count, float snr_db, unsigned long long seed,
+                    unsigned long long offset, float *d_llr, void *stream);
+/* Uniform random bits (Philox), int8 0/1. */
+int nrldpc_random_bits(int8_t *d_bits, long long count, unsigned long long seed, unsigned long long offset,
+                       void *stream);
+/*
+ * Error counters of the Monte-Carlo drivers (scripts/internal/sim_ldpc_internal.py:61-62):
+ * counters[0] += B, [1] += codeblocks whose first K decisions differ from ref, [2] += differing bits,
+ * [3] += sum of iters (if iters != NULL).  ref [B,ref_stride], got [B,got_stride] int8; counters int64[4].
+ */
+int nrldpc_count_errors(const int8_t *d_ref, long long ref_stride, const int8_t *d_got, long long got_stride,
+                        int B, int K, const int32_t *d_iters, long long *d_counters, void *stream);
+
+/* ------------------------------------------------------------------ CRC (callers' side of the path) */
+/*
+ * crc.nr_crc_encode(blk, poly) / crc.nr_crc_decode(blkandcrc, poly) with mask = 0
+ * (py5gphy/crc/crc.py:4-41, :43-88; polynomials :96-106), B blocks of A payload bits, one int8 per bit.
+ *   poly_id: 0 '6', 1 '11', 2 '16', 3 '24A', 4 '24B', 5 '24C'.  Returns the CRC length L (> 0) or an error.
+ *   encode: in [B,A] -> out [B,A+L].   check: in [B,A+L] -> err [B] uint8 (1 = CRC error).
+ */
+int nrldpc_crc_encode(const int8_t *d_in, int B, int A, int poly_id, int8_t *d_out, void *stream);
+int nrldpc_crc_check(const int8_t *d_in, int B, int A, int poly_id, uint8_t *d_err, void *stream);
+int nrldpc_crc_encode_host(const int8_t *in, int B, int A, int poly_id, int8_t *out);
+int nrldpc_crc_check_host(const int8_t *in, int B, int A, int poly_id, uint8_t *err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRLDPC_B200_H */

@@ -1,0 +1,90 @@
+"""ctypes loader of libnrldpc_b200.so (the C ABI declared in include/nrldpc_b200.h)."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libnrldpc_b200.so")
+_lib = None
+
+EINVAL, ECUDA, ENOMEM, ENODEV = -1, -2, -3, -4
+
+
+class NrLdpcError(RuntimeError):
+    """A CUDA-side failure.  Bad arguments raise AssertionError instead, like the reference does."""
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into python_5gtoolbox_b200/libnrldpc_b200.so (in-tree)."""
+    src = os.path.join(_HERE, "csrc")
+    if force:
+        subprocess.run(["make", "-C", src, "clean"], check=True, capture_output=True)
+    r = subprocess.run(["make", "-C", src, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("nvcc build of libnrldpc_b200.so failed")
+    return SO_PATH
+
+
+def _declare(L):
+    c = ctypes
+    p = c.c_void_p
+    i, f, d, ll, ull = c.c_int, c.c_float, c.c_double, c.c_longlong, c.c_ulonglong
+    ip = c.POINTER(c.c_int)
+    sigs = {
+        "nrldpc_version": (i, []),
+        "nrldpc_last_error": (c.c_char_p, []),
+        "nrldpc_device_count": (i, []),
+        "nrldpc_find_ils": (i, [i]),
+        "nrldpc_dims": (i, [i, i, ip, ip, ip, ip]),
+        "nrldpc_build_csr": (i, [i, i, p, p]),
+        "nrldpc_encode": (i, [p, i, i, i, i, p, p]),
+        "nrldpc_encode_host": (i, [p, i, i, i, i, p]),
+        "nrldpc_decode_minsum": (i, [p, i, i, i, i, f, f, i, p, p, p, p, p]),
+        "nrldpc_decode_minsum_host": (i, [p, i, i, i, i, f, f, i, p, p, p, p]),
+        "nrldpc_decode_minsum_geometry": (i, [i, i, ip, ip, ip]),
+        "nrldpc_decode_csr_host": (i, [p, i, i, i, i, p, p, i, i, d, d, i, p, p, p]),
+        "nrldpc_decode_soft_ref_host": (i, [p, i, i, i, i, i, i, d, d, i, p, p, p]),
+        "nrldpc_decode_bf_csr_host": (i, [p, i, i, i, p, p, i, p, p, p]),
+        "nrldpc_decode_bf_host": (i, [p, i, i, i, i, p, p, p]),
+        "nrldpc_awgn_llr": (i, [p, ll, f, ull, ull, p, p]),
+        "nrldpc_random_bits": (i, [p, ll, ull, ull, p]),
+        "nrldpc_count_errors": (i, [p, ll, p, ll, i, i, p, p, p]),
+        "nrldpc_crc_encode": (i, [p, i, i, i, p, p]),
+        "nrldpc_crc_check": (i, [p, i, i, i, p, p]),
+        "nrldpc_crc_encode_host": (i, [p, i, i, i, p]),
+        "nrldpc_crc_check_host": (i, [p, i, i, i, p]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)  # AttributeError here = the .so does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    return sigs
+
+
+def lib():
+    """The loaded library.  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise NrLdpcError(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  python_5gtoolbox_b200 has no CPU fallback.")
+        L = ctypes.CDLL(SO_PATH)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_declare(ctypes.CDLL(SO_PATH)).keys())
+
+
+def check(rc, what=""):
+    if rc >= 0:
+        return rc
+    msg = lib().nrldpc_last_error().decode()
+    if rc == EINVAL:
+        raise AssertionError(f"{what}: {msg}")
+    raise NrLdpcError(f"{what}: {msg} (code {rc})")

@@ -1,0 +1,333 @@
+// nrldpc_api.cu -- the extern "C" boundary of libnrldpc_b200.so (see include/nrldpc_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "nrldpc_common.cuh"
+
+namespace nrldpc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return NRLDPC_ENODEV;
+    if (e == cudaErrorMemoryAllocation) return NRLDPC_ENOMEM;
+    return NRLDPC_ECUDA;
+}
+
+// (bgn, Zc) -> quasi-cyclic tables, built once
+static const QcCfg *get_cfg(int bgn, int Zc)
+{
+    static std::mutex mu;
+    static std::map<int, QcCfg *> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    const int key = bgn * 1024 + Zc;
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    QcCfg *c = new QcCfg;
+    if (build_qc_cfg(bgn, Zc, c) != NRLDPC_OK) {
+        delete c;
+        set_error("invalid (bgn=%d, Zc=%d): bgn must be 1|2 and Zc a TS 38.212 lifting size", bgn, Zc);
+        return nullptr;
+    }
+    cache[key] = c;
+    return c;
+}
+
+// RAII device buffer for the synchronous host entry points
+struct DevBuf {
+    void *p = nullptr;
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+// CSR -> CSC (edges of every column in ascending row order = the reference's B lists,
+// py5gphy/ldpc/nr_ldpc_decode.py:88-91)
+static void csr_to_csc(int M, int Nv, const int32_t *rowptr, const int32_t *colidx, std::vector<int32_t> &cptr,
+                       std::vector<int32_t> &cedge, std::vector<int32_t> &crow)
+{
+    const int E = rowptr[M];
+    cptr.assign(Nv + 1, 0);
+    cedge.resize(E ? E : 1);
+    crow.resize(E ? E : 1);
+    for (int e = 0; e < E; ++e) cptr[colidx[e] + 1]++;
+    for (int n = 0; n < Nv; ++n) cptr[n + 1] += cptr[n];
+    std::vector<int32_t> pos(cptr.begin(), cptr.end() - 1);
+    for (int m = 0; m < M; ++m)
+        for (int e = rowptr[m]; e < rowptr[m + 1]; ++e) {
+            const int q = pos[colidx[e]]++;
+            cedge[q] = e;
+            crow[q] = m;
+        }
+}
+
+static int check_csr(int M, int Nv, const int32_t *rowptr, const int32_t *colidx)
+{
+    if (M <= 0 || Nv <= 0 || !rowptr || !colidx || rowptr[0] != 0) { set_error("bad CSR matrix"); return NRLDPC_EINVAL; }
+    for (int m = 0; m < M; ++m)
+        if (rowptr[m + 1] < rowptr[m]) { set_error("bad CSR rowptr"); return NRLDPC_EINVAL; }
+    for (int e = 0; e < rowptr[M]; ++e)
+        if (colidx[e] < 0 || colidx[e] >= Nv) { set_error("bad CSR column index"); return NRLDPC_EINVAL; }
+    return NRLDPC_OK;
+}
+
+template <typename T>
+static int soft_csr_host(const T *llr, int B, int M, int Nv, const int32_t *rowptr, const int32_t *colidx, int prepend,
+                         int max_iter, int algo, double alpha, double beta, int early_term, int8_t *ck,
+                         uint8_t *status, int32_t *iters)
+{
+    if (B < 0 || max_iter < 0 || (algo != NRLDPC_ALGO_MINSUM && algo != NRLDPC_ALGO_BP) || !llr || !ck) {
+        set_error("decode_csr: bad argument");
+        return NRLDPC_EINVAL;
+    }
+    if (int rc = check_csr(M, Nv, rowptr, colidx)) return rc;
+    if (B == 0) return NRLDPC_OK;
+    const int E = rowptr[M], Nin = Nv - prepend;
+    std::vector<int32_t> cptr, cedge, crow;
+    csr_to_csc(M, Nv, rowptr, colidx, cptr, cedge, crow);
+    DevBuf d_llr, d_rp, d_ci, d_cp, d_ce, d_work, d_ck, d_st, d_it;
+    // bound the workspace: process the batch in chunks
+    const size_t per_cb = ((size_t)E + 2 * (size_t)Nv) * sizeof(T);
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)2 << 30) / per_cb));
+    NRLDPC_CUDA(d_llr.alloc((size_t)chunk * Nin * sizeof(T)));
+    NRLDPC_CUDA(d_rp.alloc((size_t)(M + 1) * 4));
+    NRLDPC_CUDA(d_ci.alloc((size_t)(E ? E : 1) * 4));
+    NRLDPC_CUDA(d_cp.alloc((size_t)(Nv + 1) * 4));
+    NRLDPC_CUDA(d_ce.alloc((size_t)(E ? E : 1) * 4));
+    NRLDPC_CUDA(d_work.alloc((size_t)chunk * per_cb));
+    NRLDPC_CUDA(d_ck.alloc((size_t)chunk * Nv));
+    NRLDPC_CUDA(d_st.alloc((size_t)chunk));
+    NRLDPC_CUDA(d_it.alloc((size_t)chunk * 4));
+    NRLDPC_CUDA(cudaMemcpy(d_rp.p, rowptr, (size_t)(M + 1) * 4, cudaMemcpyHostToDevice));
+    NRLDPC_CUDA(cudaMemcpy(d_ci.p, colidx, (size_t)E * 4, cudaMemcpyHostToDevice));
+    NRLDPC_CUDA(cudaMemcpy(d_cp.p, cptr.data(), (size_t)(Nv + 1) * 4, cudaMemcpyHostToDevice));
+    NRLDPC_CUDA(cudaMemcpy(d_ce.p, cedge.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        NRLDPC_CUDA(cudaMemcpy(d_llr.p, llr + (size_t)b0 * Nin, (size_t)nb * Nin * sizeof(T), cudaMemcpyHostToDevice));
+        if (int rc = launch_soft_csr<T>(d_llr.as<T>(), nb, M, Nv, E, d_rp.as<int32_t>(), d_ci.as<int32_t>(),
+                                        d_cp.as<int32_t>(), d_ce.as<int32_t>(), prepend, max_iter, algo, (T)alpha,
+                                        (T)beta, early_term, d_work.as<T>(), d_ck.as<int8_t>(), d_st.as<uint8_t>(),
+                                        d_it.as<int32_t>(), 0))
+            return rc;
+        NRLDPC_CUDA(cudaMemcpy(ck + (size_t)b0 * Nv, d_ck.p, (size_t)nb * Nv, cudaMemcpyDeviceToHost));
+        if (status) NRLDPC_CUDA(cudaMemcpy(status + b0, d_st.p, (size_t)nb, cudaMemcpyDeviceToHost));
+        if (iters) NRLDPC_CUDA(cudaMemcpy(iters + b0, d_it.p, (size_t)nb * 4, cudaMemcpyDeviceToHost));
+    }
+    return NRLDPC_OK;
+}
+
+static int bf_csr_host(const double *llr, int B, int M, int Nv, const int32_t *rowptr, const int32_t *colidx, int prepend,
+                       int max_iter, int8_t *ck, uint8_t *status, int32_t *iters)
+{
+    if (B < 0 || max_iter < 0 || !llr || !ck) { set_error("decode_bf: bad argument"); return NRLDPC_EINVAL; }
+    if (int rc = check_csr(M, Nv, rowptr, colidx)) return rc;
+    if (B == 0) return NRLDPC_OK;
+    const int E = rowptr[M], Nin = Nv - prepend;
+    std::vector<int32_t> cptr, cedge, crow;
+    csr_to_csc(M, Nv, rowptr, colidx, cptr, cedge, crow);
+    DevBuf d_llr, d_rp, d_ci, d_cp, d_cr, d_work, d_ck, d_st, d_it;
+    NRLDPC_CUDA(d_llr.alloc((size_t)B * Nin * 8));
+    NRLDPC_CUDA(d_rp.alloc((size_t)(M + 1) * 4));
+    NRLDPC_CUDA(d_ci.alloc((size_t)(E ? E : 1) * 4));
+    NRLDPC_CUDA(d_cp.alloc((size_t)(Nv + 1) * 4));
+    NRLDPC_CUDA(d_cr.alloc((size_t)(E ? E : 1) * 4));
+    NRLDPC_CUDA(d_work.alloc((size_t)B * M * 4));
+    NRLDPC_CUDA(d_ck.alloc((size_t)B * Nv));
+    NRLDPC_CUDA(d_st.alloc((size_t)B));
+    NRLDPC_CUDA(d_it.alloc((size_t)B * 4));
+    NRLDPC_CUDA(cudaMemcpy(d_llr.p, llr, (size_t)B * Nin * 8, cudaMemcpyHostToDevice));
+    NRLDPC_CUDA(cudaMemcpy(d_rp.p, rowptr, (size_t)(M + 1) * 4, cudaMemcpyHostToDevice));
+    NRLDPC_CUDA(cudaMemcpy(d_ci.p, colidx, (size_t)E * 4, cudaMemcpyHostToDevice));
+    NRLDPC_CUDA(cudaMemcpy(d_cp.p, cptr.data(), (size_t)(Nv + 1) * 4, cudaMemcpyHostToDevice));
+    NRLDPC_CUDA(cudaMemcpy(d_cr.p, crow.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
+    if (int rc = launch_bf_csr(d_llr.as<double>(), B, M, Nv, E, d_rp.as<int32_t>(), d_ci.as<int32_t>(),
+                               d_cp.as<int32_t>(), d_cr.as<int32_t>(), prepend, max_iter, d_work.as<int32_t>(),
+                               d_ck.as<int8_t>(), d_st.as<uint8_t>(), d_it.as<int32_t>(), 0))
+        return rc;
+    NRLDPC_CUDA(cudaMemcpy(ck, d_ck.p, (size_t)B * Nv, cudaMemcpyDeviceToHost));
+    if (status) NRLDPC_CUDA(cudaMemcpy(status, d_st.p, (size_t)B, cudaMemcpyDeviceToHost));
+    if (iters) NRLDPC_CUDA(cudaMemcpy(iters, d_it.p, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    return NRLDPC_OK;
+}
+
+}  // namespace nrldpc
+
+using namespace nrldpc;
+
+extern "C" {
+
+int nrldpc_version(void) { return 100; }
+const char *nrldpc_last_error(void) { return g_err; }
+
+int nrldpc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int nrldpc_find_ils(int Zc) { return find_ils(Zc); }
+
+int nrldpc_dims(int bgn, int Zc, int *K, int *N, int *Nfull, int *M)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    if (K) *K = c->K;
+    if (N) *N = c->N;
+    if (Nfull) *Nfull = c->Nfull;
+    if (M) *M = c->M;
+    return NRLDPC_OK;
+}
+
+int nrldpc_build_csr(int bgn, int Zc, int32_t *rowptr, int32_t *colidx)
+{
+    if (!get_cfg(bgn, Zc) || !rowptr || !colidx) return NRLDPC_EINVAL;
+    return build_csr(bgn, Zc, rowptr, colidx);
+}
+
+int nrldpc_encode(int8_t *d_ck, int B, int bgn, int Zc, int fix_fillers, int8_t *d_dn, void *stream)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    if (B < 0 || !d_ck || !d_dn) { set_error("encode: bad argument"); return NRLDPC_EINVAL; }
+    return launch_encode(*c, d_ck, B, fix_fillers, d_dn, (cudaStream_t)stream);
+}
+
+int nrldpc_encode_host(int8_t *ck, int B, int bgn, int Zc, int fix_fillers, int8_t *dn)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    if (B < 0 || !ck || !dn) { set_error("encode: bad argument"); return NRLDPC_EINVAL; }
+    if (B == 0) return NRLDPC_OK;
+    DevBuf d_ck, d_dn;
+    NRLDPC_CUDA(d_ck.alloc((size_t)B * c->K));
+    NRLDPC_CUDA(d_dn.alloc((size_t)B * c->N));
+    NRLDPC_CUDA(cudaMemcpy(d_ck.p, ck, (size_t)B * c->K, cudaMemcpyHostToDevice));
+    if (int rc = launch_encode(*c, d_ck.as<int8_t>(), B, fix_fillers, d_dn.as<int8_t>(), 0)) return rc;
+    NRLDPC_CUDA(cudaMemcpy(dn, d_dn.p, (size_t)B * c->N, cudaMemcpyDeviceToHost));
+    if (fix_fillers) NRLDPC_CUDA(cudaMemcpy(ck, d_ck.p, (size_t)B * c->K, cudaMemcpyDeviceToHost));
+    return NRLDPC_OK;
+}
+
+int nrldpc_decode_minsum(const float *d_llr, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
+                         int early_term, int8_t *d_ck, uint32_t *d_info_packed, uint8_t *d_status, int32_t *d_iters,
+                         void *stream)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    if (B < 0 || max_iter < 0 || !d_llr) { set_error("decode_minsum: bad argument"); return NRLDPC_EINVAL; }
+    return launch_decode_minsum(*c, d_llr, B, max_iter, alpha, beta, early_term, d_ck, d_info_packed, d_status,
+                                d_iters, (cudaStream_t)stream);
+}
+
+int nrldpc_decode_minsum_geometry(int bgn, int Zc, int *cbs_per_cta, int *threads, int *smem_bytes)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    return decode_minsum_geometry(*c, cbs_per_cta, threads, smem_bytes);
+}
+
+// Host-buffer entry point: double-buffered chunks so that (with pinned host memory) the H2D copy of
+// chunk i+1 and the D2H copy of chunk i-1 overlap the decode of chunk i.
+int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
+                              int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    if (B < 0 || max_iter < 0 || !llr) { set_error("decode_minsum: bad argument"); return NRLDPC_EINVAL; }
+    if (B == 0) return NRLDPC_OK;
+    const size_t llr_bytes = (size_t)c->N * 4, nwords = (size_t)(c->K + 31) / 32;
+    int chunk = (int)std::max<size_t>(1, ((size_t)192 << 20) / llr_bytes);
+    if (chunk > B) chunk = B;
+    struct Stage {
+        DevBuf llr, ck, info, st, it;
+        cudaStream_t s = nullptr;
+        ~Stage() { if (s) cudaStreamDestroy(s); }
+    } st[2];
+    const int nstage = B > chunk ? 2 : 1;
+    for (int i = 0; i < nstage; ++i) {
+        NRLDPC_CUDA(cudaStreamCreateWithFlags(&st[i].s, cudaStreamNonBlocking));
+        NRLDPC_CUDA(st[i].llr.alloc((size_t)chunk * llr_bytes));
+        if (ck) NRLDPC_CUDA(st[i].ck.alloc((size_t)chunk * c->Nfull));
+        if (info_packed) NRLDPC_CUDA(st[i].info.alloc((size_t)chunk * nwords * 4));
+        NRLDPC_CUDA(st[i].st.alloc((size_t)chunk));
+        NRLDPC_CUDA(st[i].it.alloc((size_t)chunk * 4));
+    }
+    int k = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
+        Stage &S = st[k % nstage];
+        const int nb = std::min(chunk, B - b0);
+        NRLDPC_CUDA(cudaMemcpyAsync(S.llr.p, llr + (size_t)b0 * c->N, (size_t)nb * llr_bytes, cudaMemcpyHostToDevice, S.s));
+        if (int rc = launch_decode_minsum(*c, S.llr.as<float>(), nb, max_iter, alpha, beta, early_term,
+                                          ck ? S.ck.as<int8_t>() : nullptr, info_packed ? S.info.as<uint32_t>() : nullptr,
+                                          S.st.as<uint8_t>(), S.it.as<int32_t>(), S.s))
+            return rc;
+        if (ck) NRLDPC_CUDA(cudaMemcpyAsync(ck + (size_t)b0 * c->Nfull, S.ck.p, (size_t)nb * c->Nfull, cudaMemcpyDeviceToHost, S.s));
+        if (info_packed)
+            NRLDPC_CUDA(cudaMemcpyAsync(info_packed + (size_t)b0 * nwords, S.info.p, (size_t)nb * nwords * 4, cudaMemcpyDeviceToHost, S.s));
+        if (status) NRLDPC_CUDA(cudaMemcpyAsync(status + b0, S.st.p, (size_t)nb, cudaMemcpyDeviceToHost, S.s));
+        if (iters) NRLDPC_CUDA(cudaMemcpyAsync(iters + b0, S.it.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, S.s));
+    }
+    for (int i = 0; i < nstage; ++i) NRLDPC_CUDA(cudaStreamSynchronize(st[i].s));
+    return NRLDPC_OK;
+}
+
+int nrldpc_decode_csr_host(const void *llr, int is_f64, int B, int M, int Nv, const int32_t *rowptr,
+                           const int32_t *colidx, int max_iter, int algo, double alpha, double beta, int early_term,
+                           int8_t *ck, uint8_t *status, int32_t *iters)
+{
+    if (is_f64)
+        return soft_csr_host<double>((const double *)llr, B, M, Nv, rowptr, colidx, 0, max_iter, algo, alpha, beta,
+                                     early_term, ck, status, iters);
+    return soft_csr_host<float>((const float *)llr, B, M, Nv, rowptr, colidx, 0, max_iter, algo, alpha, beta,
+                                early_term, ck, status, iters);
+}
+
+int nrldpc_decode_soft_ref_host(const void *llr, int is_f64, int B, int bgn, int Zc, int max_iter, int algo,
+                                double alpha, double beta, int early_term, int8_t *ck, uint8_t *status, int32_t *iters)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    const int nnz = (bgn == 1 ? 316 : 197) * Zc;
+    std::vector<int32_t> rowptr(c->M + 1), colidx(nnz);
+    build_csr(bgn, Zc, rowptr.data(), colidx.data());
+    if (is_f64)
+        return soft_csr_host<double>((const double *)llr, B, c->M, c->Nfull, rowptr.data(), colidx.data(), 2 * Zc,
+                                     max_iter, algo, alpha, beta, early_term, ck, status, iters);
+    return soft_csr_host<float>((const float *)llr, B, c->M, c->Nfull, rowptr.data(), colidx.data(), 2 * Zc, max_iter,
+                                algo, alpha, beta, early_term, ck, status, iters);
+}
+
+int nrldpc_decode_bf_csr_host(const double *llr, int B, int M, int Nv, const int32_t *rowptr, const int32_t *colidx,
+                              int max_iter, int8_t *ck, uint8_t *status, int32_t *iters)
+{
+    return bf_csr_host(llr, B, M, Nv, rowptr, colidx, 0, max_iter, ck, status, iters);
+}
+
+int nrldpc_decode_bf_host(const double *llr, int B, int bgn, int Zc, int max_iter, int8_t *ck, uint8_t *status,
+                          int32_t *iters)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    const int nnz = (bgn == 1 ? 316 : 197) * Zc;
+    std::vector<int32_t> rowptr(c->M + 1), colidx(nnz);
+    build_csr(bgn, Zc, rowptr.data(), colidx.data());
+    return bf_csr_host(llr, B, c->M, c->Nfull, rowptr.data(), colidx.data(), 2 * Zc, max_iter, ck, status, iters);
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+// nrldpc_util.cu -- device-side Monte-Carlo helpers: Philox bits, BPSK/AWGN LLRs, error counters.
+// Replaces the per-codeblock host loop of for_test_5g_ldpc_encoder (py5gphy/ldpc/nr_ldpc_decode.py:247-257)
+// and the np.array_equal bookkeeping of scripts/internal/sim_ldpc_internal.py:61-62.
+#include "nrldpc_common.cuh"
+
+namespace nrldpc {
+
+namespace {
+
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so any (seed, offset) slice is reproducible
+// on any number of GPUs.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ uint4 philox_at(unsigned long long seed, unsigned long long block)
+{
+    return philox4x32_10(make_uint4((uint32_t)block, (uint32_t)(block >> 32), 0x4c445043u, 0u),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+__global__ void random_bits_kernel(int8_t *bits, long long count, unsigned long long seed, unsigned long long offset)
+{
+    // one Philox block = 128 bits -> 128 outputs
+    const long long nblk = (count + 127) / 128;
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+        const uint4 x = philox_at(seed, offset + (unsigned long long)b);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+        const long long base = b * 128;
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+            if (base + i < count) bits[base + i] = (int8_t)((w[i >> 5] >> (i & 31)) & 1u);
+    }
+}
+
+__global__ void awgn_llr_kernel(const int8_t *__restrict__ dn, long long count, float sigma, float scale,
+                                unsigned long long seed, unsigned long long offset, float *__restrict__ llr)
+{
+    const long long nblk = (count + 3) / 4;
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+        const uint4 x = philox_at(seed ^ 0x9E3779B97F4A7C15ull, offset + (unsigned long long)b);
+        // Box-Muller on two uniform pairs
+        const float u0 = ((x.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((x.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float u2 = ((x.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((x.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+        float s0, c0, s1, c1;
+        sincospif(2.0f * u1, &s0, &c0);
+        sincospif(2.0f * u3, &s1, &c1);
+        const float n[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+        const long long base = b * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (base + i < count) {
+                const int d = dn[base + i];
+                // :252-257  en = 1 - 2 dn ; fn = en + N(0, sigma) ; LLR = 2 fn / sigma^2
+                llr[base + i] = d < 0 ? 0.0f : scale * ((1.0f - 2.0f * (float)d) + sigma * n[i]);
+            }
+    }
+}
+
+__global__ void count_errors_kernel(const int8_t *__restrict__ ref, long long ref_stride, const int8_t *__restrict__ got,
+                                    long long got_stride, int B, int K, const int32_t *__restrict__ iters,
+                                    unsigned long long *__restrict__ counters)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long blk = 0, bit = 0, its = 0, n = 0;
+    for (int b = warp; b < B; b += nwarps) {
+        int diff = 0;
+        for (int k = lane; k < K; k += 32) diff += ref[b * ref_stride + k] != got[b * got_stride + k];
+        diff = __reduce_add_sync(0xffffffffu, diff);
+        if (lane == 0) {
+            ++n; bit += diff; blk += diff != 0;
+            if (iters) its += iters[b];
+        }
+    }
+    if (lane == 0 && n) {
+        atomicAdd(counters + 0, n);
+        atomicAdd(counters + 1, blk);
+        atomicAdd(counters + 2, bit);
+        atomicAdd(counters + 3, its);
+    }
+}
+
+
+// nr_crc_encode / nr_crc_decode long division (py5gphy/crc/crc.py:28-33, :72-77), one thread per block
+// of bits.  rem holds the L-bit remainder register, MSB = remainder[0].  mode 0: append the CRC to
+// `in` [B,A] -> out [B,A+L].  mode 1: `in` is [B,A+L]; err[b] = remainder != 0.
+__global__ void crc_kernel(const int8_t *__restrict__ in, int B, int A, int L, uint32_t poly, int mode,
+                           int8_t *__restrict__ out, uint8_t *__restrict__ err)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int len_in = mode ? A + L : A;
+    const int8_t *x = in + (size_t)b * len_in;
+    const uint32_t mask = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+    uint32_t rem = 0;
+    for (int k = 0; k < L; ++k) rem = (rem << 1) | (uint32_t)((k < len_in) ? (x[k] & 1) : 0);
+    for (int idx = 0; idx < A; ++idx) {
+        const uint32_t first = (rem >> (L - 1)) & 1u;
+        const int k = idx + L;
+        rem = ((rem << 1) & mask) | (uint32_t)((k < len_in) ? (x[k] & 1) : 0);
+        if (first) rem ^= poly;
+    }
+    if (mode == 0) {
+        int8_t *y = out + (size_t)b * (A + L);
+        for (int k = 0; k < A; ++k) y[k] = x[k];
+        for (int k = 0; k < L; ++k) y[A + k] = (int8_t)((rem >> (L - 1 - k)) & 1u);
+    } else {
+        err[b] = rem != 0;
+    }
+}
+
+}  // namespace
+
+}  // namespace nrldpc
+
+using namespace nrldpc;
+
+extern "C" int nrldpc_random_bits(int8_t *d_bits, long long count, unsigned long long seed, unsigned long long offset,
+                                  void *stream)
+{
+    if (count <= 0) return NRLDPC_OK;
+    const long long nblk = (count + 127) / 128;
+    const int grid = (int)((nblk + 255) / 256 > 148 * 16 ? 148 * 16 : (nblk + 255) / 256);
+    random_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_bits, count, seed, offset);
+    NRLDPC_CUDA(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_awgn_llr(const int8_t *d_dn, long long count, float snr_db, unsigned long long seed,
+                               unsigned long long offset, float *d_llr, void *stream)
+{
+    if (count <= 0) return NRLDPC_OK;
+    const double sigma = pow(10.0, -(double)snr_db / 20.0), np = pow(10.0, -(double)snr_db / 10.0);
+    const long long nblk = (count + 3) / 4;
+    const int grid = (int)((nblk + 255) / 256 > 148 * 32 ? 148 * 32 : (nblk + 255) / 256);
+    awgn_llr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_dn, count, (float)sigma, (float)(2.0 / np), seed, offset, d_llr);
+    NRLDPC_CUDA(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_count_errors(const int8_t *d_ref, long long ref_stride, const int8_t *d_got, long long got_stride,
+                                   int B, int K, const int32_t *d_iters, long long *d_counters, void *stream)
+{
+    if (B <= 0) return NRLDPC_OK;
+    const int grid = (B + 7) / 8 > 148 * 8 ? 148 * 8 : (B + 7) / 8;
+    count_errors_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_ref, ref_stride, d_got, got_stride, B, K, d_iters,
+                                                               reinterpret_cast<unsigned long long *>(d_counters));
+    NRLDPC_CUDA(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+// polynomial bit patterns of py5gphy/crc/crc.py:96-106 (x^L term dropped), MSB = first array element
+static int crc_poly(int poly_id, int *L, uint32_t *poly)
+{
+    static const int len[6] = {6, 11, 16, 24, 24, 24};
+    static const uint32_t pat[6] = {0x21u, 0x621u, 0x1021u, 0x864CFBu, 0x800063u, 0xB2B117u};
+    if (poly_id < 0 || poly_id > 5) { set_error("crc: poly_id must be 0..5 ('6','11','16','24A','24B','24C')"); return NRLDPC_EINVAL; }
+    *L = len[poly_id];
+    *poly = pat[poly_id];
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_crc_encode(const int8_t *d_in, int B, int A, int poly_id, int8_t *d_out, void *stream)
+{
+    int L; uint32_t poly;
+    if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
+    if (B < 0 || A < 0 || !d_in || !d_out) { set_error("crc_encode: bad argument"); return NRLDPC_EINVAL; }
+    if (B == 0) return NRLDPC_OK;
+    crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 0, d_out, nullptr);
+    NRLDPC_CUDA(cudaGetLastError());
+    return L;
+}
+
+extern "C" int nrldpc_crc_check(const int8_t *d_in, int B, int A, int poly_id, uint8_t *d_err, void *stream)
+{
+    int L; uint32_t poly;
+    if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
+    if (B < 0 || A < 0 || !d_in || !d_err) { set_error("crc_check: bad argument"); return NRLDPC_EINVAL; }
+    if (B == 0) return NRLDPC_OK;
+    crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 1, nullptr, d_err);
+    NRLDPC_CUDA(cudaGetLastError());
+    return L;
+}
+
+namespace {
+struct TmpBuf {
+    void *p = nullptr;
+    ~TmpBuf() { if (p) cudaFree(p); }
+};
+}
+
+extern "C" int nrldpc_crc_encode_host(const int8_t *in, int B, int A, int poly_id, int8_t *out)
+{
+    int L; uint32_t poly;
+    if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
+    if (B <= 0 || A < 0) return B == 0 ? L : NRLDPC_EINVAL;
+    TmpBuf di, dout;
+    NRLDPC_CUDA(cudaMalloc(&di.p, (size_t)B * A + 1));
+    NRLDPC_CUDA(cudaMalloc(&dout.p, (size_t)B * (A + L)));
+    NRLDPC_CUDA(cudaMemcpy(di.p, in, (size_t)B * A, cudaMemcpyHostToDevice));
+    int rc = nrldpc_crc_encode((const int8_t *)di.p, B, A, poly_id, (int8_t *)dout.p, nullptr);
+    if (rc < 0) return rc;
+    NRLDPC_CUDA(cudaMemcpy(out, dout.p, (size_t)B * (A + L), cudaMemcpyDeviceToHost));
+    return L;
+}
+
+extern "C" int nrldpc_crc_check_host(const int8_t *in, int B, int A, int poly_id, uint8_t *err)
+{
+    int L; uint32_t poly;
+    if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
+    if (B <= 0 || A < 0) return B == 0 ? L : NRLDPC_EINVAL;
+    TmpBuf di, de;
+    NRLDPC_CUDA(cudaMalloc(&di.p, (size_t)B * (A + L)));
+    NRLDPC_CUDA(cudaMalloc(&de.p, (size_t)B));
+    NRLDPC_CUDA(cudaMemcpy(di.p, in, (size_t)B * (A + L), cudaMemcpyHostToDevice));
+    int rc = nrldpc_crc_check((const int8_t *)di.p, B, A, poly_id, (uint8_t *)de.p, nullptr);
+    if (rc < 0) return rc;
+    NRLDPC_CUDA(cudaMemcpy(err, de.p, (size_t)B, cudaMemcpyDeviceToHost));
+    return L;
+}

@@ -1,0 +1,216 @@
+"""Batched LDPC entry points over the C ABI (include/nrldpc_b200.h).
+
+NumPy arrays go through the ``*_host`` entry points (H2D / kernels / D2H inside, synchronous);
+CUDA ``torch.Tensor`` arguments are used in place through their ``data_ptr()`` on torch's current
+stream (PyTorch is only the allocator / stream provider).  One (bgn, Zc) per call, like one
+transport block in the reference (py5gphy/ldpc/ldpc_info.py:62-69).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+ALGO_MINSUM, ALGO_BP = 0, 1
+
+
+def dims(bgn, Zc):
+    """(K, N, N', M) of py5gphy/ldpc/nr_ldpc_decode.py:26-31."""
+    assert bgn in [1, 2]
+    assert _lib.lib().nrldpc_find_ils(int(Zc)) < 8
+    K, N, Nf, M = (ctypes.c_int() for _ in range(4))
+    _lib.check(_lib.lib().nrldpc_dims(bgn, int(Zc), K, N, Nf, M), "dims")
+    return K.value, N.value, Nf.value, M.value
+
+
+def find_iLS(Zc):
+    return _lib.lib().nrldpc_find_ils(int(Zc))
+
+
+def csr(Zc, bgn):
+    """Sparse getH (py5gphy/ldpc/ldpc_info.py:99-139): (rowptr int32[M+1], colidx int32[E])."""
+    K, N, Nf, M = dims(bgn, Zc)
+    E = (316 if bgn == 1 else 197) * Zc
+    rowptr = np.empty(M + 1, np.int32)
+    colidx = np.empty(E, np.int32)
+    n = _lib.check(_lib.lib().nrldpc_build_csr(bgn, int(Zc), rowptr.ctypes.data, colidx.ctypes.data), "build_csr")
+    assert n == E
+    return rowptr, colidx
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------ encoder
+
+def encode_batch(ck, bgn, Zc=None, fix_fillers=True):
+    """nr_ldpc_encode.encode_ldpc for B codeblocks (py5gphy/ldpc/nr_ldpc_encode.py:8-50).
+
+    ck: int8 [B,K] with -1 fillers (NumPy array or CUDA tensor); mutated in place (fillers -> 0) when
+    fix_fillers, which is the reference's side effect.  Returns dn int8 [B,N] of the same kind.
+    """
+    assert bgn in [1, 2]
+    assert ck.ndim == 2
+    B, K = ck.shape
+    if Zc is None:
+        Zc = K // 22 if bgn == 1 else K // 10
+    Kx, N, Nf, M = dims(bgn, Zc)
+    assert K == Kx
+    L = _lib.lib()
+    if _is_torch(ck):
+        import torch
+        assert ck.is_cuda and ck.dtype == torch.int8 and ck.is_contiguous()
+        dn = torch.empty((B, N), dtype=torch.int8, device=ck.device)
+        with torch.cuda.device(ck.device):
+            _lib.check(L.nrldpc_encode(ck.data_ptr(), B, bgn, Zc, int(fix_fillers), dn.data_ptr(), _stream_ptr()), "encode")
+        return dn
+    assert ck.dtype == np.int8 and ck.flags.c_contiguous
+    dn = np.empty((B, N), np.int8)
+    _lib.check(L.nrldpc_encode_host(ck.ctypes.data, B, bgn, Zc, int(fix_fillers), dn.ctypes.data), "encode")
+    return dn
+
+
+# ------------------------------------------------------------------ min-sum decoder
+
+def decode_batch(llr, Zc, bgn, L, alpha=1.0, beta=0.0, early_term=True, want_ck=True, want_info=False):
+    """nr_decode_ldpc(..., 'min-sum', alpha, beta) for B codeblocks in fp32
+    (py5gphy/ldpc/nr_ldpc_decode.py:11-49,51-143,178-227).
+
+    llr: float32 [B,N], NumPy (host path) or CUDA tensor (device path, async on the current stream).
+    Returns dict(ck=int8[B,N'] | None, info=uint32[B,ceil(K/32)] | None, status=bool/uint8[B], iters=int32[B]).
+    """
+    assert bgn in [1, 2]
+    K, N, Nf, M = dims(bgn, Zc)
+    assert llr.ndim == 2 and llr.shape[1] == N
+    B = llr.shape[0]
+    nw = (K + 31) // 32
+    Lb = _lib.lib()
+    if _is_torch(llr):
+        import torch
+        assert llr.is_cuda and llr.dtype == torch.float32 and llr.is_contiguous()
+        dev = llr.device
+        ck = torch.empty((B, Nf), dtype=torch.int8, device=dev) if want_ck else None
+        info = torch.empty((B, nw), dtype=torch.int32, device=dev) if want_info else None
+        status = torch.empty((B,), dtype=torch.uint8, device=dev)
+        iters = torch.empty((B,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(Lb.nrldpc_decode_minsum(llr.data_ptr(), B, bgn, int(Zc), int(L), float(alpha), float(beta),
+                                               int(bool(early_term)), ck.data_ptr() if want_ck else None,
+                                               info.data_ptr() if want_info else None, status.data_ptr(),
+                                               iters.data_ptr(), _stream_ptr()), "decode_minsum")
+        return dict(ck=ck, info=info, status=status, iters=iters)
+    llr = np.ascontiguousarray(llr, np.float32)
+    ck = np.empty((B, Nf), np.int8) if want_ck else None
+    info = np.empty((B, nw), np.uint32) if want_info else None
+    status = np.empty(B, np.uint8)
+    iters = np.empty(B, np.int32)
+    _lib.check(Lb.nrldpc_decode_minsum_host(llr.ctypes.data, B, bgn, int(Zc), int(L), float(alpha), float(beta),
+                                            int(bool(early_term)), ck.ctypes.data if want_ck else None,
+                                            info.ctypes.data if want_info else None, status.ctypes.data,
+                                            iters.ctypes.data), "decode_minsum")
+    return dict(ck=ck, info=info, status=status.astype(bool), iters=iters)
+
+
+def decode_ref_batch(llr, Zc, bgn, L, algo="min-sum", alpha=1.0, beta=0.0, early_term=True, f64=True):
+    """The generic (CSR) kernels on the 5G matrix; f64=True reproduces the reference's float64
+    arithmetic exactly for 'min-sum'.  NumPy in / out.  Returns (ck int8[B,N'], status bool[B], iters int32[B])."""
+    K, N, Nf, M = dims(bgn, Zc)
+    llr = np.ascontiguousarray(llr, np.float64 if f64 else np.float32)
+    assert llr.ndim == 2 and llr.shape[1] == N
+    B = llr.shape[0]
+    ck = np.empty((B, Nf), np.int8)
+    status = np.empty(B, np.uint8)
+    iters = np.empty(B, np.int32)
+    a = {"min-sum": ALGO_MINSUM, "BP": ALGO_BP}[algo]
+    _lib.check(_lib.lib().nrldpc_decode_soft_ref_host(llr.ctypes.data, int(f64), B, bgn, int(Zc), int(L), a, float(alpha),
+                                                      float(beta), int(bool(early_term)), ck.ctypes.data,
+                                                      status.ctypes.data, iters.ctypes.data), "decode_soft_ref")
+    return ck, status.astype(bool), iters
+
+
+def decode_csr_batch(llr, rowptr, colidx, Nv, L, algo="min-sum", alpha=1.0, beta=0.0, early_term=True, f64=True):
+    """decode_ldpc on an arbitrary CSR H (py5gphy/ldpc/nr_ldpc_decode.py:51-143)."""
+    llr = np.ascontiguousarray(np.atleast_2d(llr), np.float64 if f64 else np.float32)
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    colidx = np.ascontiguousarray(colidx, np.int32)
+    B, M = llr.shape[0], rowptr.size - 1
+    assert llr.shape[1] == Nv
+    ck = np.empty((B, Nv), np.int8)
+    status = np.empty(B, np.uint8)
+    iters = np.empty(B, np.int32)
+    a = {"min-sum": ALGO_MINSUM, "BP": ALGO_BP}[algo]
+    _lib.check(_lib.lib().nrldpc_decode_csr_host(llr.ctypes.data, int(f64), B, M, int(Nv), rowptr.ctypes.data,
+                                                 colidx.ctypes.data, int(L), a, float(alpha), float(beta),
+                                                 int(bool(early_term)), ck.ctypes.data, status.ctypes.data,
+                                                 iters.ctypes.data), "decode_csr")
+    return ck, status.astype(bool), iters
+
+
+def decode_bf_batch(llr, Zc, bgn, L):
+    """nr_decode_ldpc(..., algo='BF') for B codeblocks (py5gphy/ldpc/ldpc_decoder_bit_flipping.py:5-73)."""
+    K, N, Nf, M = dims(bgn, Zc)
+    llr = np.ascontiguousarray(np.atleast_2d(llr), np.float64)
+    assert llr.shape[1] == N
+    B = llr.shape[0]
+    ck = np.empty((B, Nf), np.int8)
+    status = np.empty(B, np.uint8)
+    iters = np.empty(B, np.int32)
+    _lib.check(_lib.lib().nrldpc_decode_bf_host(llr.ctypes.data, B, bgn, int(Zc), int(L), ck.ctypes.data,
+                                                status.ctypes.data, iters.ctypes.data), "decode_bf")
+    return ck, status.astype(bool), iters
+
+
+def decode_bf_csr_batch(llr, rowptr, colidx, Nv, L):
+    llr = np.ascontiguousarray(np.atleast_2d(llr), np.float64)
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    colidx = np.ascontiguousarray(colidx, np.int32)
+    B, M = llr.shape[0], rowptr.size - 1
+    assert llr.shape[1] == Nv
+    ck = np.empty((B, Nv), np.int8)
+    status = np.empty(B, np.uint8)
+    iters = np.empty(B, np.int32)
+    _lib.check(_lib.lib().nrldpc_decode_bf_csr_host(llr.ctypes.data, B, M, int(Nv), rowptr.ctypes.data,
+                                                    colidx.ctypes.data, int(L), ck.ctypes.data, status.ctypes.data,
+                                                    iters.ctypes.data), "decode_bf_csr")
+    return ck, status.astype(bool), iters
+
+
+# ------------------------------------------------------------------ device-side Monte-Carlo helpers (torch tensors)
+
+def random_bits(B, n, seed, device, offset=0):
+    import torch
+    out = torch.empty((B, n), dtype=torch.int8, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().nrldpc_random_bits(out.data_ptr(), B * n, int(seed), int(offset), _stream_ptr()), "random_bits")
+    return out
+
+
+def awgn_llr(dn, snr_db, seed, offset=0, out=None):
+    """BPSK + AWGN + LLR of for_test_5g_ldpc_encoder (py5gphy/ldpc/nr_ldpc_decode.py:252-257) on device."""
+    import torch
+    assert dn.is_cuda and dn.dtype == torch.int8 and dn.is_contiguous()
+    if out is None:
+        out = torch.empty(dn.shape, dtype=torch.float32, device=dn.device)
+    with torch.cuda.device(dn.device):
+        _lib.check(_lib.lib().nrldpc_awgn_llr(dn.data_ptr(), dn.numel(), float(snr_db), int(seed), int(offset),
+                                              out.data_ptr(), _stream_ptr()), "awgn_llr")
+    return out
+
+
+def count_errors(ref, got, K, iters=None, counters=None):
+    """counters int64[4] += {codeblocks, block errors, bit errors, iterations} (sim_ldpc_internal.py:61-62)."""
+    import torch
+    B = ref.shape[0]
+    if counters is None:
+        counters = torch.zeros(4, dtype=torch.int64, device=ref.device)
+    with torch.cuda.device(ref.device):
+        _lib.check(_lib.lib().nrldpc_count_errors(ref.data_ptr(), ref.stride(0), got.data_ptr(), got.stride(0), B, int(K),
+                                                  iters.data_ptr() if iters is not None else None,
+                                                  counters.data_ptr(), _stream_ptr()), "count_errors")
+    return counters

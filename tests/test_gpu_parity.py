@@ -1,0 +1,313 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle, the committed golden
+fixtures of the live reference, and size-independent properties at the headline size.
+
+Bars: encoder / BF / CRC / fp64 min-sum bit-exact; fp32 min-sum identical hard decisions, status and
+iteration counts on every golden vector and on >= 99.99% of random codeblocks (north_star)."""
+import numpy as np
+import pytest
+
+from tests.conftest import ZLIST, hex_to_bits
+from tests.golden import kat_appendix_c as KAT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from python_5gtoolbox_b200 import engine, _lib
+    assert _lib.lib().nrldpc_device_count() > 0, "no CUDA device: the GPU tests cannot run (and there is no CPU fallback)"
+    return engine
+
+
+def _rand_ck(rng, bgn, Zc, B, fillers=True):
+    K = (22 if bgn == 1 else 10) * Zc
+    ck = rng.integers(0, 2, (B, K)).astype("i1")
+    if fillers:
+        for b in range(B):
+            F = int(rng.integers(0, Zc))
+            if F:
+                ck[b, K - F:] = -1
+    return ck
+
+
+def _awgn(rng, dn, snr_db):
+    sigma = 10 ** (-snr_db / 20)
+    fn = (1 - 2 * dn.astype(np.float64)) + rng.normal(0, sigma, dn.shape)
+    return (2 * fn / sigma ** 2).astype(np.float32)
+
+
+# ------------------------------------------------------------------ encoder
+
+def test_encode_golden(eng, enc_golden):
+    for g in enc_golden:
+        ck = g["ck"].copy().reshape(1, -1)
+        dn = eng.encode_batch(ck, g["bgn"])
+        assert np.array_equal(dn[0], g["dn"]), (g["bgn"], g["Zc"])
+        assert np.array_equal(ck[0], g["ck_after"])
+
+
+@pytest.mark.parametrize("bgn", [1, 2])
+def test_encode_all_lifting_sizes_vs_oracle(eng, oracle, bgn):
+    rng = np.random.default_rng(100 + bgn)
+    for Zc in ZLIST:
+        B = 64 if Zc <= 64 else 9
+        ck = _rand_ck(rng, bgn, Zc, B)
+        a, b = ck.copy(), ck.copy()
+        dn = eng.encode_batch(a, bgn)
+        ref = oracle.encode_batch(b, bgn, Zc)
+        assert np.array_equal(dn, ref), (bgn, Zc)
+        assert np.array_equal(a, b)
+        a = ck.copy()
+        eng.encode_batch(a, bgn, fix_fillers=False)
+        assert np.array_equal(a, ck)
+
+
+@pytest.mark.parametrize("case", KAT.ENC, ids=lambda c: f"bg{c[0]}z{c[1]}")
+def test_encode_kat(eng, case):
+    bgn, Zc, K, F, hin, N, hdn, fidx = case
+    ck = hex_to_bits(hin, K).copy().reshape(1, -1)
+    if F:
+        ck[0, K - F:] = -1
+    dn = eng.encode_batch(ck, bgn)[0]
+    assert sorted(np.nonzero(dn == -1)[0].tolist()) == fidx
+    dn[dn == -1] = 0
+    assert np.array_equal(dn, hex_to_bits(hdn, N))
+
+
+def test_encode_parity_check_property_headline(eng):
+    """H [c;w]^T = 0 (mod 2) at BG1 Zc=384 for a large batch, on a torch device tensor."""
+    import torch
+    Zc, bgn, B = 384, 1, 512
+    ck = eng.random_bits(B, 22 * Zc, seed=7, device="cuda")
+    dn = eng.encode_batch(ck, bgn)
+    cw = torch.cat([ck[:, :2 * Zc], dn], 1).cpu().numpy().astype(np.int64)
+    rp, ci = eng.csr(Zc, bgn)
+    synd = np.add.reduceat(cw[:, ci], rp[:-1], axis=1) % 2
+    assert not synd.any()
+    # linearity over GF(2): enc(a ^ b) = enc(a) ^ enc(b)
+    a, b = ck[:8], ck[8:16]
+    assert torch.equal(eng.encode_batch((a ^ b).contiguous(), bgn), eng.encode_batch(a.contiguous(), bgn) ^ eng.encode_batch(b.contiguous(), bgn))
+
+
+# ------------------------------------------------------------------ min-sum decoder
+
+def test_decode_golden_fp32(eng, dec_golden):
+    """fp32 hot kernel vs the reference's float64 outputs on the committed vectors."""
+    bad = []
+    n = 0
+    for g in dec_golden:
+        if g["algo"] != "min-sum":
+            continue
+        r = eng.decode_batch(g["llr"][None, :], g["Zc"], g["bgn"], g["L"], g["alpha"], g["beta"], True)
+        ok = np.array_equal(r["ck"][0], g["ck"]) and bool(r["status"][0]) == g["status"] and int(r["iters"][0]) == g["iters"]
+        n += 1
+        if not ok:
+            bad.append((g["bgn"], g["Zc"], g["seed"], int((r["ck"][0] != g["ck"]).sum()), int(r["iters"][0]), g["iters"]))
+    assert n >= 100 and not bad, bad
+
+
+def test_decode_golden_fp64_exact(eng, dec_golden):
+    for g in dec_golden:
+        if g["algo"] != "min-sum" or g["Zc"] > 128:
+            continue
+        ck, st, it = eng.decode_ref_batch(g["llr"][None, :].astype(np.float64), g["Zc"], g["bgn"], g["L"], "min-sum",
+                                          g["alpha"], g["beta"], True, f64=True)
+        assert np.array_equal(ck[0], g["ck"]) and bool(st[0]) == g["status"] and int(it[0]) == g["iters"], (g["bgn"], g["Zc"])
+
+
+@pytest.mark.parametrize("case", [c for c in KAT.DEC if c[0] == "min-sum"], ids=lambda c: f"bg{c[1]}z{c[2]}L{c[3]}")
+def test_decode_kat_dyadic_bit_exact(eng, oracle, case):
+    algo, bgn, Zc, L, alpha, beta, hin, flips, status, iters, hck = case
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    dn = oracle.encode_ldpc(hex_to_bits(hin, K).copy(), bgn)
+    llr = (4.0 * (1 - 2 * dn.astype(np.float32)))
+    llr[flips] *= -0.5
+    r = eng.decode_batch(llr[None, :], Zc, bgn, L, alpha, beta, True)
+    assert np.array_equal(r["ck"][0], hex_to_bits(hck, Nf)) and bool(r["status"][0]) == status and int(r["iters"][0]) == iters
+
+
+@pytest.mark.parametrize("bgn", [1, 2])
+def test_decode_all_lifting_sizes_vs_oracle(eng, oracle, bgn):
+    """Every Zc: fp32 kernel == fp32 oracle bit for bit (same arithmetic), and == fp64 oracle on
+    >= 99.99% of codeblocks overall (hard bits, status, iterations)."""
+    rng = np.random.default_rng(500 + bgn)
+    tot = diff64 = 0
+    for zi, Zc in enumerate(ZLIST):
+        B = 48 if Zc <= 32 else (16 if Zc <= 128 else 6)
+        ck = _rand_ck(rng, bgn, Zc, B, fillers=False)
+        dn = oracle.encode_batch(ck.copy(), bgn, Zc)
+        snr = (0.3 if bgn == 1 else -2.3) + 0.4 * (zi % 3)
+        llr = _awgn(rng, dn, snr)
+        L, alpha, beta = [(10, 0.8, 0.0), (16, 1.0, 0.5), (12, 0.8, 0.3), (8, 1.0, 0.0)][zi % 4]
+        r = eng.decode_batch(llr, Zc, bgn, L, alpha, beta, True, want_info=True)
+        c32, s32, i32 = oracle.decode_batch(llr, Zc, bgn, L, "min-sum", alpha, beta, 1, np.float32)
+        assert np.array_equal(r["ck"], c32) and np.array_equal(r["status"], s32) and np.array_equal(r["iters"], i32), (bgn, Zc)
+        K = eng.dims(bgn, Zc)[0]
+        info = np.unpackbits(r["info"].view(np.uint8), axis=1, bitorder="little")[:, :K]
+        assert np.array_equal(info, r["ck"][:, :K])
+        c64, s64, i64 = oracle.decode_batch(llr.astype(np.float64), Zc, bgn, L, "min-sum", alpha, beta, 1, np.float64)
+        same = (r["ck"] == c64).all(1) & (r["status"] == s64) & (r["iters"] == i64)
+        tot += B
+        diff64 += int((~same).sum())
+    assert diff64 <= max(0, int(tot * 1e-4)), (diff64, tot)
+
+
+def test_decode_fixed_iterations_and_edge_cases(eng, oracle):
+    rng = np.random.default_rng(9)
+    for bgn, Zc in [(1, 12), (2, 20), (1, 96)]:
+        K, N, Nf, M = eng.dims(bgn, Zc)
+        dn = oracle.encode_batch(_rand_ck(rng, bgn, Zc, 5, fillers=False), bgn, Zc)
+        llr = _awgn(rng, dn, 1.0 if bgn == 1 else -1.5)
+        for L in (0, 1, 7):
+            for et in (0, 1):
+                r = eng.decode_batch(llr, Zc, bgn, L, 0.8, 0.0, bool(et))
+                c, s, i = oracle.decode_batch(llr, Zc, bgn, L, "min-sum", 0.8, 0.0, et, np.float32)
+                assert np.array_equal(r["ck"], c) and np.array_equal(r["status"], s) and np.array_equal(r["iters"], i), (bgn, Zc, L, et)
+        # all-zero LLRs, exact ties, -0.0 inputs
+        z = np.zeros((2, N), np.float32)
+        z[1, ::2] = -0.0
+        r = eng.decode_batch(z, Zc, bgn, 3, 0.8, 0.2, True)
+        c, s, i = oracle.decode_batch(z, Zc, bgn, 3, "min-sum", 0.8, 0.2, 1, np.float32)
+        assert np.array_equal(r["ck"], c) and np.array_equal(r["status"], s) and np.array_equal(r["iters"], i)
+    # empty batch
+    r = eng.decode_batch(np.zeros((0, 66 * 12), np.float32), 12, 1, 4)
+    assert r["ck"].shape == (0, 68 * 12)
+    with pytest.raises(AssertionError):
+        eng.decode_batch(np.zeros((1, 10), np.float32), 12, 1, 4)
+    with pytest.raises(AssertionError):
+        eng.decode_batch(np.zeros((1, 66 * 17), np.float32), 17, 1, 4)
+
+
+def test_decode_headline_roundtrip_device(eng):
+    """BG1 Zc=384: encode -> AWGN -> decode on device tensors; every converged codeblock satisfies all
+    parity checks and (at this SNR) equals what was sent; a noiseless batch decodes in 0 iterations."""
+    import torch
+    Zc, bgn, B = 384, 1, 296
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    ck = eng.random_bits(B, K, seed=11, device="cuda")
+    dn = eng.encode_batch(ck, bgn)
+    llr = eng.awgn_llr(dn, 1.5, seed=3)
+    r = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, True)
+    torch.cuda.synchronize()
+    st = r["status"].bool()
+    assert st.float().mean() > 0.95
+    cw = torch.cat([ck[:, :2 * Zc], dn], 1)
+    assert torch.equal(r["ck"][st], cw[st])
+    assert int(r["iters"].min()) >= 1 and int(r["iters"].max()) <= 10
+    cnt = eng.count_errors(ck, r["ck"], K, r["iters"])
+    assert cnt.tolist()[0] == B and cnt.tolist()[1] == int((~st).sum()) or cnt.tolist()[1] <= int((~st).sum())
+    # throughput mode (no early exit) reaches the same codewords on the converged blocks
+    r2 = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, False)
+    assert int(r2["iters"].min()) == 10
+    assert torch.equal(r2["ck"][st], cw[st])
+    clean = (1 - 2 * dn.float()) * 8
+    r3 = eng.decode_batch(clean.contiguous(), Zc, bgn, 10, 0.8, 0.0, True)
+    assert int(r3["iters"].max()) == 1 and bool(r3["status"].all())  # punctured bits need one pass
+
+
+# ------------------------------------------------------------------ BF / BP / CRC / generic H
+
+def test_bf_vs_oracle_and_golden(eng, oracle, dec_golden):
+    for g in dec_golden:
+        if g["algo"] != "BF":
+            continue
+        ck, st, _ = eng.decode_bf_batch(g["llr"][None, :].astype(np.float64), g["Zc"], g["bgn"], g["L"])
+        assert np.array_equal(ck[0], g["ck"]) and bool(st[0]) == g["status"]
+    rng = np.random.default_rng(3)
+    for bgn, Zc, snr in [(1, 2, 4.0), (2, 6, 2.0), (1, 10, 4.5), (2, 36, 3.0), (1, 64, 5.0)]:
+        dn = oracle.encode_batch(_rand_ck(rng, bgn, Zc, 6, fillers=False), bgn, Zc)
+        llr = _awgn(rng, dn, snr).astype(np.float64)
+        ck, st, it = eng.decode_bf_batch(llr, Zc, bgn, 12)
+        for b in range(6):
+            _, c, s, i = oracle.nr_decode_ldpc(llr[b], Zc, bgn, 12, "BF")
+            assert np.array_equal(ck[b], c) and bool(st[b]) == s and int(it[b]) == i
+
+
+@pytest.mark.parametrize("case", [c for c in KAT.DEC if c[0] == "BF"], ids=lambda c: f"bg{c[1]}z{c[2]}")
+def test_bf_kat(eng, oracle, case):
+    algo, bgn, Zc, L, _, _, hin, flips, status, _, hck = case
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    dn = oracle.encode_ldpc(hex_to_bits(hin, K).copy(), bgn)
+    llr = 4.0 * (1 - 2 * dn.astype(np.float64))
+    llr[flips] *= -0.5
+    ck, st, _ = eng.decode_bf_batch(llr[None, :], Zc, bgn, L)
+    assert np.array_equal(ck[0], hex_to_bits(hck, Nf)) and bool(st[0]) == status
+
+
+def test_generic_h_toy_matrix(eng, oracle):
+    """Arbitrary (non-QC) H: the toy 4x6 matrix style of ldpc_decoder_bit_flipping.py:115-131."""
+    H = np.array([[1, 1, 0, 1, 0, 0], [0, 1, 1, 0, 1, 0], [1, 0, 0, 0, 1, 1], [0, 0, 1, 1, 0, 1]], "i1")
+    rp, ci = oracle.dense_to_csr(H)
+    rng = np.random.default_rng(5)
+    llr = rng.normal(2.0, 2.0, (40, 6))
+    for alpha, beta in [(1, 0), (0.8, 0), (1, 0.3), (0.7, 0.2)]:
+        ck, st, it = eng.decode_csr_batch(llr, rp, ci, 6, 8, "min-sum", alpha, beta, True, f64=True)
+        for b in range(40):
+            c, s, i = oracle.decode_ldpc(llr[b], H, 8, "min-sum", alpha, beta)
+            assert np.array_equal(ck[b], c) and bool(st[b]) == s and int(it[b]) == i
+    ck, st, it = eng.decode_bf_csr_batch(llr, rp, ci, 6, 5)
+    for b in range(40):
+        c, s, i = oracle.decode_ldpc(llr[b], H, 5, "BF")
+        assert np.array_equal(ck[b], c) and bool(st[b]) == s
+
+
+def test_bp_golden(eng, dec_golden):
+    n = 0
+    for g in dec_golden:
+        if g["algo"] != "BP":
+            continue
+        ck, st, it = eng.decode_ref_batch(g["llr"][None, :].astype(np.float64), g["Zc"], g["bgn"], g["L"], "BP", 1, 0, True, f64=True)
+        assert np.array_equal(ck[0], g["ck"]) and bool(st[0]) == g["status"] and int(it[0]) == g["iters"]
+        n += 1
+    assert n >= 10
+
+
+def test_crc_golden(eng):
+    import os
+    from tests.conftest import GOLDEN
+    from python_5gtoolbox_b200 import crc
+    with np.load(os.path.join(GOLDEN, "crc_golden.npz")) as z:
+        for k in [k for k in z.files if k.startswith("in_")]:
+            _, poly, n = k.split("_")
+            out = crc.nr_crc_encode(z[k], poly)
+            assert np.array_equal(out, z[f"out_{poly}_{n}"]), k
+            assert crc.nr_crc_decode(out, poly)[1] == 0
+            bad = out.copy()
+            bad[0] ^= 1
+            assert crc.nr_crc_decode(bad, poly)[1] == 1
+    # crc.py:170-210 style: masked CRC round trip
+    blk = np.array([1, 1, 1, 1, 0, 0, 0, 0], "i1")
+    enc = crc.nr_crc_encode(blk, "16", 12345)
+    assert crc.nr_crc_decode(enc, "16", 12345)[1] == 0 and crc.nr_crc_decode(enc, "16", 0)[1] == 1
+
+
+# ------------------------------------------------------------------ drop-in modules
+
+def test_dropin_modules_match_oracle(eng, oracle):
+    from python_5gtoolbox_b200.ldpc import nr_ldpc_decode, nr_ldpc_encode, ldpc_info
+    np.random.seed(42)
+    for bgn, Zc, snr in [(1, 6, 0.5), (2, 12, -2.0)]:
+        blk, dn, llr = nr_ldpc_decode.for_test_5g_ldpc_encoder(Zc, bgn, snr)
+        assert np.array_equal(dn, oracle.encode_ldpc(blk.copy(), bgn))
+        assert np.array_equal(blk, oracle.nr_crc_encode(blk[:-24], "24A"))
+        llr = llr.astype("f4").astype("f8")
+        for algo, a, b in [("min-sum", 0.8, 0.3), ("BF", 1, 0), ("BP", 1, 0)]:
+            out, ck, st = nr_ldpc_decode.nr_decode_ldpc(llr, Zc, bgn, 10, algo, a, b)
+            o2, c2, s2, _ = oracle.nr_decode_ldpc(llr, Zc, bgn, 10, algo, a, b)
+            assert np.array_equal(ck, c2) and st == s2 and out.size == (22 if bgn == 1 else 10) * Zc
+            assert ck.dtype == (np.float64 if algo == "BF" else np.int8)
+        H = ldpc_info.getH(Zc, bgn, ldpc_info.find_iLS(Zc))
+        full = np.concatenate([np.zeros(2 * Zc), llr])
+        ck, st = nr_ldpc_decode.decode_ldpc(full, H, 10, "min-sum", 0.8, 0.3)
+        assert np.array_equal(ck, oracle.nr_decode_ldpc(llr, Zc, bgn, 10, "min-sum", 0.8, 0.3)[1])
+        ck, st = nr_ldpc_decode.decode_ldpc(full, np.asarray(H), 10, "min-sum", 0.8, 0.3)  # untagged -> generic fp64
+        assert np.array_equal(ck, oracle.nr_decode_ldpc(llr, Zc, bgn, 10, "min-sum", 0.8, 0.3)[1])
+    with pytest.raises(AssertionError):
+        nr_ldpc_decode.nr_decode_ldpc(np.zeros(10), 6, 1, 4)
+    with pytest.raises(AssertionError):
+        nr_ldpc_decode.nr_decode_ldpc(np.zeros(66 * 6), 6, 1, 4, "layered")
+    ck = np.zeros(44, "i1")
+    ck[40:] = -1
+    view = ck[:]
+    dn = nr_ldpc_encode.encode_ldpc(view, 1)
+    assert (ck[40:] == 0).all() and (dn[36:40] == -1).all()
