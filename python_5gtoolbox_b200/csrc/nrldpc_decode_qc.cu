@@ -19,24 +19,59 @@
 //   posterior: LQ_ext = fl(LLR + Lr), Lq_ext = fl(LQ_ext - Lr), with the LLR re-read from L2.
 // The three zero-input cases of _min_sum_process (:188-225) fall out of the record with sign(0) := +.
 //
-// Mapping: a CTA owns G codeblocks; a warp processes "tiles" = (row-block or column-block, 32
-// consecutive lifted indices r); the circulant shift is the shared-memory index rotation (r+P) mod Zc,
-// conflict-free because a warp reads 32 consecutive words.  For Zc < 32 several codeblocks share a warp.
+// Mapping: a CTA owns G codeblocks.  Every thread owns ONE (codeblock, lifted index r) for the whole
+// kernel; its warp walks a fixed subset of the row-blocks (check pass) and core column-blocks
+// (variable pass), so per-tile index arithmetic disappears and the per-edge tables (byte offsets,
+// built on the host, passed by value in the constant bank) are warp-uniform.  The circulant shift is
+// the shared-memory index rotation (r+P) mod Zc: conflict-free, 32 consecutive words per warp.
+// For Zc < 32 several codeblocks share a warp.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
 #include "nrldpc_common.cuh"
 
 namespace nrldpc {
 
 namespace {
 
+struct RowInfo {
+    uint32_t mag_off;   // byte offset of the row-block's float2 magnitudes inside a codeblock slot
+    uint32_t bits_off;  // byte offset of its sign/index words
+    uint32_t ext_llr;   // float index of the extension column's LLRs inside a codeblock's LLR row
+    uint16_t e0;        // first edge in cn_edge
+    uint8_t deg, wide;
+};
+struct ColInfo {
+    uint32_t lq_off;   // byte offset of the column-block's posteriors inside a slot
+    uint32_t llr_off;  // float index of its channel LLRs, or kNoLlr for the punctured columns
+    uint16_t q0;       // first entry in vn_entry
+    uint8_t nwide, deg;
+};
+constexpr uint32_t kNoLlr = 0xffffffffu;
+
+// Everything the kernel needs, by value (constant bank).
+struct DecTab {
+    int Zc, Z4, Z8, nrows, ncore, kb, K, N, Nfull, tiles, lanes, lanes_log2, per;
+    int G, ncolumns, S, nwarps;
+    int slot_bytes, off_mags, off_bits, off_ext;
+    uint2 cn_edge[kMaxEdges];      // {byte offset of the column's LQ array, shift * 4}
+    RowInfo row[kMaxRows];
+    uint4 vn_entry[kMaxCoreEdges]; // {row mag_off, row bits_off, ((Zc - shift) % Zc) * 8, k << idxshift | (31 - bitpos)}
+    ColInfo col[kMaxCore];
+    uint8_t cn_order[kMaxRows], vn_order[kMaxCore];
+};
+
 struct DecArgs {
     const float *llr;
-    int B, G, max_iter, early_term;
+    int B, max_iter;
     float alpha, beta;
     int8_t *ck;
     uint32_t *info;
     uint8_t *status;
     int32_t *iters;
-    int slot_bytes, off_mags, off_bits, off_ext;
 };
 
 constexpr int kMaxG = 32;
@@ -50,76 +85,63 @@ __device__ __forceinline__ float min_xorsign_abs(float a, float b)
     return d;
 }
 
-// Check-to-variable message of edge k decoded from a row record.
-// WIDE: idx at bit 24, else at bit 12; sign of edge k at bit `bitpos`.
-__device__ __forceinline__ float record_lr(float2 m, uint32_t bits, int idx, int k, int bitpos)
+// Check-to-variable message decoded from a row record: magnitude m.y on the argmin edge (isidx),
+// m.x elsewhere; `signword` carries the edge's sign in bit 31.
+__device__ __forceinline__ float record_lr(float2 m, bool isidx, uint32_t signword)
 {
-    const float mag = (idx == k) ? m.y : m.x;
-    return __uint_as_float(__float_as_uint(mag) ^ (((bits >> bitpos) & 1u) << 31));
+    const float mag = isidx ? m.y : m.x;
+    return __uint_as_float(__float_as_uint(mag) ^ (signword & 0x80000000u));
 }
 
-struct Lane {
-    int g;        // codeblock slot inside the CTA
-    int r;        // lifted index (clamped to 0 when inactive)
-    int cb;       // global codeblock (clamped to B-1 when inactive)
-    bool active;  // this lane owns a real (codeblock, r) that is still being decoded
+struct Me {            // what a thread owns for the whole kernel
+    char *slot;        // its codeblock's shared-memory slot
+    const float *llr;  // its codeblock's LLR row, already offset by r
+    int g, r;          // slot index, lifted index (clamped to a valid value when !valid)
+    bool valid;
 };
-
-// Decompose tile-column `col` (0 .. G*tiles/per) into the lane's codeblock slot and lifted index.
-__device__ __forceinline__ Lane lane_of(const QcCfg &c, const DecArgs &a, int col, int lane, uint32_t donemask)
-{
-    Lane L;
-    const int g = (col / c.tiles) * c.per + (lane >> c.lanes_log2);
-    const int r = (col % c.tiles) * 32 + (lane & (c.lanes - 1));
-    const int cb = blockIdx.x * a.G + g;
-    L.active = (r < c.Zc) && (g < a.G) && (cb < a.B) && !((donemask >> (g & 31)) & 1u);
-    L.g = (g < a.G) ? g : 0;
-    L.r = (r < c.Zc) ? r : 0;
-    L.cb = (cb < a.B) ? cb : a.B - 1;
-    return L;
-}
 
 // One check row (row-block i, lifted index r): syndrome bit of the current hard decisions, then the
 // min-sum update of its record from Lq = LQ - Lr_old.  py5gphy/ldpc/nr_ldpc_decode.py:107-123,178-227.
-template <int DEG, bool EXT, bool WIDE>
-__device__ __forceinline__ void cn_row(const QcCfg &c, const DecArgs &a, char *slot, int i, const Lane &L,
-                                       int lane, int *flag)
+template <int DEG, bool EXT, bool WIDE, bool ET>
+__device__ __forceinline__ void cn_row(const DecTab &T, const DecArgs &a, const Me &me, const int i, const bool active,
+                                       int *flag)
 {
-    const int Zc = c.Zc, r = L.r;
-    const int e0 = c.rowptr[i];
-    float2 *mp = reinterpret_cast<float2 *>(slot + a.off_mags) + i * Zc + r;
-    char *bp = slot + a.off_bits + c.bits_off[i] * Zc;
-    const float2 m = *mp;
-    const uint32_t bits = WIDE ? reinterpret_cast<uint32_t *>(bp)[r] : reinterpret_cast<uint16_t *>(bp)[r];
-    const int idx = bits >> (WIDE ? 24 : 12);
+    constexpr int SH = WIDE ? 24 : 12;
+    constexpr uint32_t IDXMASK = WIDE ? 0x1f000000u : 0xf000u;
+    const uint32_t r4 = (uint32_t)me.r * 4u;
+    const uint32_t e0 = T.row[i].e0;
+    char *rec = me.slot + T.row[i].mag_off + 2 * r4;
+    char *bp = me.slot + T.row[i].bits_off + (WIDE ? r4 : r4 >> 1);
+    const float2 m = *reinterpret_cast<const float2 *>(rec);
+    const uint32_t bits = WIDE ? *reinterpret_cast<const uint32_t *>(bp) : *reinterpret_cast<const uint16_t *>(bp);
     float llr_e = 0.f;
-    if (EXT) llr_e = __fadd_rn(__ldg(a.llr + (size_t)L.cb * c.N + (size_t)(c.kb + i - 2) * Zc + r), 0.0f);
-    const float *LQ = reinterpret_cast<const float *>(slot);
+    if (EXT) llr_e = __fadd_rn(__ldg(me.llr + T.row[i].ext_llr), 0.0f);
 
     float vmin = __uint_as_float(kInfBits);  // sign = running sign product, |vmin| = first minimum
     float min2 = vmin;
-    int nidx = 0;
-    uint32_t sacc = 0, synd = 0;
+    uint32_t nidx = 0, sacc = 0, synd = 0;
 #pragma unroll
     for (int k = 0; k < DEG; ++k) {
-        const float lr = record_lr(m, bits, idx, k, DEG - 1 - k);
+        const bool isidx = ((bits ^ ((uint32_t)k << SH)) & IDXMASK) == 0;
+        const float lr = record_lr(m, isidx, bits << (31 - (DEG - 1 - k)));
         float x;
         if (EXT && k == DEG - 1) {
             x = __fadd_rn(llr_e, lr);  // posterior of the degree-1 extension variable (:126)
-            const uint32_t hb = __ballot_sync(0xffffffffu, x < 0.f);
-            if (L.active && (r & (c.lanes - 1)) == 0)
-                reinterpret_cast<uint32_t *>(slot + a.off_ext)[(i - 4) * c.tiles + (r >> 5)] = hb;
+            if (ET) {
+                const uint32_t hb = __ballot_sync(0xffffffffu, x < 0.f);
+                if (active && (me.r & (T.lanes - 1)) == 0)
+                    reinterpret_cast<uint32_t *>(me.slot + T.off_ext)[(i - 4) * T.tiles + (me.r >> 5)] = hb;
+            }
         } else {
-            const uint32_t ew = c.edge[e0 + k];
-            int cc = r + (int)(ew >> 8);
-            if (cc >= Zc) cc -= Zc;
-            x = LQ[(ew & 0xff) * Zc + cc];
+            const uint2 ew = T.cn_edge[e0 + k];
+            const uint32_t t = r4 + ew.y;
+            x = *reinterpret_cast<const float *>(me.slot + ew.x + min(t, t - (uint32_t)T.Z4));
         }
-        synd ^= __float_as_uint(x);           // sign bit = hard decision LQ<0 (:107-108)
+        if (ET) synd ^= __float_as_uint(x);   // sign bit = hard decision LQ<0 (:107-108)
         const float q = __fsub_rn(x, lr);     // Lq = LQ - Lr (:131)
         const float aq = fabsf(q), a1 = fabsf(vmin);
         min2 = fminf(min2, fmaxf(a1, aq));
-        nidx = (aq < a1) ? k : nidx;
+        nidx = (aq < a1) ? (uint32_t)k << SH : nidx;
         vmin = min_xorsign_abs(vmin, q);
         sacc = __funnelshift_l(__float_as_uint(q), sacc, 1);  // sign of Lq on edge k -> bit DEG-1-k
     }
@@ -127,110 +149,126 @@ __device__ __forceinline__ void cn_row(const QcCfg &c, const DecArgs &a, char *s
     const float mag1 = __fmul_rn(a.alpha, fmaxf(__fsub_rn(fabsf(vmin), a.beta), 0.f));
     const float mag2 = __fmul_rn(a.alpha, fmaxf(__fsub_rn(min2, a.beta), 0.f));
     const uint32_t sp = (uint32_t)((int)__float_as_uint(vmin) >> 31);
-    const uint32_t nb = ((sacc ^ sp) & ((1u << DEG) - 1u)) | ((uint32_t)nidx << (WIDE ? 24 : 12));
-    if (L.active) {
-        *mp = make_float2(mag1, mag2);
-        if (WIDE) reinterpret_cast<uint32_t *>(bp)[r] = nb;
-        else reinterpret_cast<uint16_t *>(bp)[r] = (uint16_t)nb;
-        if (synd >> 31) flag[L.g] = 1;
+    const uint32_t nb = ((sacc ^ sp) & ((1u << DEG) - 1u)) | nidx;
+    if (active) {
+        *reinterpret_cast<float2 *>(rec) = make_float2(mag1, mag2);
+        if (WIDE) *reinterpret_cast<uint32_t *>(bp) = nb;
+        else *reinterpret_cast<uint16_t *>(bp) = (uint16_t)nb;
+        if (ET && (synd >> 31)) flag[me.g] = 1;
     }
 }
 
-__device__ __forceinline__ void cn_dispatch(const QcCfg &c, const DecArgs &a, char *slot, int i, const Lane &L,
-                                            int lane, int *flag)
+template <bool ET>
+__device__ __forceinline__ void cn_dispatch(const DecTab &T, const DecArgs &a, const Me &me, int i, bool active, int *flag)
 {
-    const int deg = c.rowptr[i + 1] - c.rowptr[i];
+    const int deg = T.row[i].deg;
     if (i < 4) {
         switch (deg) {
-        case 19: cn_row<19, false, true>(c, a, slot, i, L, lane, flag); break;
-        case 10: cn_row<10, false, false>(c, a, slot, i, L, lane, flag); break;
-        default: cn_row<8, false, false>(c, a, slot, i, L, lane, flag); break;
+        case 19: cn_row<19, false, true, ET>(T, a, me, i, active, flag); break;
+        case 10: cn_row<10, false, false, ET>(T, a, me, i, active, flag); break;
+        default: cn_row<8, false, false, ET>(T, a, me, i, active, flag); break;
         }
     } else {
         switch (deg) {
-        case 3: cn_row<3, true, false>(c, a, slot, i, L, lane, flag); break;
-        case 4: cn_row<4, true, false>(c, a, slot, i, L, lane, flag); break;
-        case 5: cn_row<5, true, false>(c, a, slot, i, L, lane, flag); break;
-        case 6: cn_row<6, true, false>(c, a, slot, i, L, lane, flag); break;
-        case 7: cn_row<7, true, false>(c, a, slot, i, L, lane, flag); break;
-        case 8: cn_row<8, true, false>(c, a, slot, i, L, lane, flag); break;
-        case 9: cn_row<9, true, false>(c, a, slot, i, L, lane, flag); break;
-        default: cn_row<10, true, false>(c, a, slot, i, L, lane, flag); break;
+        case 3: cn_row<3, true, false, ET>(T, a, me, i, active, flag); break;
+        case 4: cn_row<4, true, false, ET>(T, a, me, i, active, flag); break;
+        case 5: cn_row<5, true, false, ET>(T, a, me, i, active, flag); break;
+        case 6: cn_row<6, true, false, ET>(T, a, me, i, active, flag); break;
+        case 7: cn_row<7, true, false, ET>(T, a, me, i, active, flag); break;
+        case 8: cn_row<8, true, false, ET>(T, a, me, i, active, flag); break;
+        case 9: cn_row<9, true, false, ET>(T, a, me, i, active, flag); break;
+        default: cn_row<10, true, false, ET>(T, a, me, i, active, flag); break;
         }
     }
 }
 
-// One core variable (column-block j, lifted index cc): LQ = LLRin + sum_i Lr(i) in ascending
+// One core variable (column-block j, lifted index c = me.r): LQ = LLRin + sum_i Lr(i) in ascending
 // row-block order = ascending check index (py5gphy/ldpc/nr_ldpc_decode.py:126).
-__device__ __forceinline__ void vn_col(const QcCfg &c, const DecArgs &a, char *slot, int j, const Lane &L)
+__device__ __forceinline__ void vn_col(const DecTab &T, const Me &me, int j, bool active)
 {
-    const int Zc = c.Zc, cc = L.r;
+    const ColInfo ci = T.col[j];
     float lv = 0.f;  // the 2Zc punctured systematic bits start at LLR 0 (:43)
-    if (j >= 2) lv = __fadd_rn(__ldg(a.llr + (size_t)L.cb * c.N + (size_t)(j - 2) * Zc + cc), 0.0f);
-    const float2 *mags = reinterpret_cast<const float2 *>(slot + a.off_mags);
-    const char *bbase = slot + a.off_bits;
+    if (ci.llr_off != kNoLlr) lv = __fadd_rn(__ldg(me.llr + ci.llr_off), 0.0f);
+    const uint32_t c8 = (uint32_t)me.r * 8u, Z8 = (uint32_t)T.Z8;
     float acc = 0.f;
-    const int q1 = c.colptr[j + 1];
-    for (int q = c.colptr[j]; q < q1; ++q) {
-        const uint32_t en = c.centry[q];
-        const int i = en & 63, k = (en >> 6) & 31, bitpos = (en >> 11) & 31;
-        int r = cc + (int)(en >> 16);
-        if (r >= Zc) r -= Zc;
-        const float2 m = mags[i * Zc + r];
-        const char *bp = bbase + c.bits_off[i] * Zc;
-        uint32_t bits;
-        int idx;
-        if (c.wide[i]) { bits = reinterpret_cast<const uint32_t *>(bp)[r]; idx = bits >> 24; }
-        else { bits = reinterpret_cast<const uint16_t *>(bp)[r]; idx = bits >> 12; }
-        acc = __fadd_rn(acc, record_lr(m, bits, idx, k, bitpos));
+    int q = ci.q0;
+    const int qw = q + ci.nwide, qe = q + ci.deg;
+    for (; q < qw; ++q) {  // rows with 32-bit sign words (BG1 rows 0-3) come first: ascending row order
+        const uint4 en = T.vn_entry[q];
+        const uint32_t t = c8 + en.z, r8 = min(t, t - Z8);
+        const float2 m = *reinterpret_cast<const float2 *>(me.slot + en.x + r8);
+        const uint32_t bits = *reinterpret_cast<const uint32_t *>(me.slot + en.y + (r8 >> 1));
+        acc = __fadd_rn(acc, record_lr(m, ((bits ^ en.w) & 0x1f000000u) == 0, bits << (en.w & 31u)));
     }
-    if (L.active) reinterpret_cast<float *>(slot)[j * Zc + cc] = __fadd_rn(lv, acc);
+#pragma unroll 4
+    for (; q < qe; ++q) {
+        const uint4 en = T.vn_entry[q];
+        const uint32_t t = c8 + en.z, r8 = min(t, t - Z8);
+        const float2 m = *reinterpret_cast<const float2 *>(me.slot + en.x + r8);
+        const uint32_t bits = *reinterpret_cast<const uint16_t *>(me.slot + en.y + (r8 >> 2));
+        acc = __fadd_rn(acc, record_lr(m, ((bits ^ en.w) & 0xf000u) == 0, bits << (en.w & 31u)));
+    }
+    if (active) *reinterpret_cast<float *>(me.slot + ci.lq_off + (c8 >> 1)) = __fadd_rn(lv, acc);
 }
 
-// Final syndrome with the post-loop tie rule LQ<=0 -> 1 (py5gphy/ldpc/nr_ldpc_decode.py:134-143).
-__device__ __forceinline__ void final_row(const QcCfg &c, const DecArgs &a, char *slot, int i, const Lane &L,
-                                          int *flag)
+// Syndrome pass without a record update.  FINAL: the post-loop tie rule LQ<=0 -> 1
+// (py5gphy/ldpc/nr_ldpc_decode.py:134-143); otherwise LQ<0 -> 1 (:107-111).  Also stores the hard
+// decisions of the extension variables, which have no resident posterior.
+template <bool FINAL>
+__device__ __forceinline__ void syndrome_row(const DecTab &T, const Me &me, int i, bool active, int *flag)
 {
-    const int Zc = c.Zc, r = L.r;
-    const int e0 = c.rowptr[i], deg = c.rowptr[i + 1] - e0;
-    const float *LQ = reinterpret_cast<const float *>(slot);
-    const int ncoredeg = (i >= 4) ? deg - 1 : deg;
+    const RowInfo ri = T.row[i];
+    const uint32_t r4 = (uint32_t)me.r * 4u;
+    const int ncoredeg = (i >= 4) ? ri.deg - 1 : ri.deg;
     uint32_t synd = 0;
     for (int k = 0; k < ncoredeg; ++k) {
-        const uint32_t ew = c.edge[e0 + k];
-        int cc = r + (int)(ew >> 8);
-        if (cc >= Zc) cc -= Zc;
-        synd ^= (LQ[(ew & 0xff) * Zc + cc] <= 0.f) ? 1u : 0u;
+        const uint2 ew = T.cn_edge[ri.e0 + k];
+        const uint32_t t = r4 + ew.y;
+        const float x = *reinterpret_cast<const float *>(me.slot + ew.x + min(t, t - (uint32_t)T.Z4));
+        synd ^= (FINAL ? (x <= 0.f) : (x < 0.f)) ? 1u : 0u;
     }
     if (i >= 4) {
-        const float2 m = reinterpret_cast<const float2 *>(slot + a.off_mags)[i * Zc + r];
-        const uint32_t bits = reinterpret_cast<const uint16_t *>(slot + a.off_bits + c.bits_off[i] * Zc)[r];
-        const float lr = record_lr(m, bits, bits >> 12, deg - 1, 0);
-        const float llr_e = __fadd_rn(__ldg(a.llr + (size_t)L.cb * c.N + (size_t)(c.kb + i - 2) * Zc + r), 0.0f);
-        const bool hb1 = __fadd_rn(llr_e, lr) <= 0.f;
+        const float2 m = *reinterpret_cast<const float2 *>(me.slot + ri.mag_off + 2 * r4);
+        const uint32_t bits = *reinterpret_cast<const uint16_t *>(me.slot + ri.bits_off + (r4 >> 1));
+        const float lr = record_lr(m, ((bits ^ ((uint32_t)(ri.deg - 1) << 12)) & 0xf000u) == 0, bits << 31);
+        const float x = __fadd_rn(__fadd_rn(__ldg(me.llr + ri.ext_llr), 0.0f), lr);
+        const bool hb1 = FINAL ? (x <= 0.f) : (x < 0.f);
         const uint32_t hb = __ballot_sync(0xffffffffu, hb1);
-        if (L.active && (r & (c.lanes - 1)) == 0)
-            reinterpret_cast<uint32_t *>(slot + a.off_ext)[(i - 4) * c.tiles + (r >> 5)] = hb;
+        if (active && (me.r & (T.lanes - 1)) == 0)
+            reinterpret_cast<uint32_t *>(me.slot + T.off_ext)[(i - 4) * T.tiles + (me.r >> 5)] = hb;
         synd ^= hb1 ? 1u : 0u;
     }
-    if (L.active && synd) flag[L.g] = 1;
+    if (active && synd) flag[me.g] = 1;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 1)
-decode_minsum_kernel(const __grid_constant__ QcCfg c, const __grid_constant__ DecArgs a)
+template <int MAXNT, bool ET>
+__global__ void __launch_bounds__(MAXNT, 1)
+decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ DecArgs a)
 {
     extern __shared__ __align__(16) char smem[];
     __shared__ int s_flag[2][kMaxG];
-    const int Zc = c.Zc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NT / 32;
-    const int G = a.G, cb0 = blockIdx.x * G;
-    const int ncolumns = (G / c.per) * c.tiles;  // warp-tile columns across the CTA's codeblocks
+    const int Zc = T.Zc, tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
+    const int warp = __reduce_min_sync(0xffffffffu, tid >> 5);  // REDUX result lives in a uniform register
+    const int G = T.G, cb0 = blockIdx.x * G;
+
+    // ---- the (codeblock, r) this thread owns, and the row-/column-block subset of its warp
+    const int colm = warp % T.ncolumns, sub = warp / T.ncolumns;
+    Me me;
+    {
+        const int g = (colm / T.tiles) * T.per + (lane >> T.lanes_log2);
+        const int r = (colm % T.tiles) * 32 + (lane & (T.lanes - 1));
+        const int cb = cb0 + g;
+        me.valid = (r < Zc) && (cb < a.B);
+        me.g = g;
+        me.r = (r < Zc) ? r : 0;
+        me.slot = smem + g * T.slot_bytes;
+        me.llr = a.llr + (size_t)((cb < a.B) ? cb : a.B - 1) * T.N + me.r;
+    }
 
     // ---- init: records = 0 (Lr = 0, :101), LQ = LLRin (:94) with the punctured columns at 0 (:43)
     {
         uint32_t *w = reinterpret_cast<uint32_t *>(smem);
-        const int nw = G * a.slot_bytes / 4;
+        const int nw = G * T.slot_bytes / 4;
         for (int t = tid; t < nw; t += NT) w[t] = 0;
         if (tid < kMaxG) { s_flag[0][tid] = 0; s_flag[1][tid] = 0; }
     }
@@ -239,13 +277,12 @@ decode_minsum_kernel(const __grid_constant__ QcCfg c, const __grid_constant__ De
     for (int g = 0; g < G; ++g)
         if (cb0 + g >= a.B) donemask |= 1u << g;
     const uint32_t fullmask = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
-    for (int t = warp; t < (c.ncore - 2) * ncolumns; t += NW) {
-        const int j = 2 + t / ncolumns;
-        const Lane L = lane_of(c, a, t % ncolumns, lane, donemask);
-        if (L.active)
-            reinterpret_cast<float *>(smem + L.g * a.slot_bytes)[j * Zc + L.r] =
-                __fadd_rn(__ldg(a.llr + (size_t)L.cb * c.N + (size_t)(j - 2) * Zc + L.r), 0.0f);
-    }
+    if (me.valid)
+        for (int o = sub; o < T.ncore; o += T.S) {
+            const ColInfo ci = T.col[o];
+            if (ci.llr_off != kNoLlr)
+                *reinterpret_cast<float *>(me.slot + ci.lq_off + me.r * 4) = __fadd_rn(__ldg(me.llr + ci.llr_off), 0.0f);
+        }
     __syncthreads();
 
     uint32_t et_mask = 0;  // codeblocks that left through the in-loop syndrome check (tie rule LQ<0)
@@ -253,41 +290,34 @@ decode_minsum_kernel(const __grid_constant__ QcCfg c, const __grid_constant__ De
     int it = 0;
     for (; it < a.max_iter; ++it) {
         int *flag = s_flag[it & 1];
-        // ---- check-node pass (+ syndrome of the current hard decisions)
-        for (int t = warp; t < c.nrows * ncolumns; t += NW) {
-            const int i = c.cn_order[t / ncolumns];
-            const Lane L = lane_of(c, a, t % ncolumns, lane, donemask);
-            cn_dispatch(c, a, smem + L.g * a.slot_bytes, i, L, lane, flag);
-        }
+        const bool active = me.valid && !((donemask >> me.g) & 1u);
+        // ---- check-node pass (+ syndrome of the current hard decisions when ET)
+        if (__any_sync(0xffffffffu, active))
+            for (int o = sub; o < T.nrows; o += T.S) cn_dispatch<ET>(T, a, me, T.cn_order[o], active, flag);
         __syncthreads();
-        if (a.early_term) {
+        if (ET) {
             for (int g = 0; g < G; ++g)
                 if (!((donemask >> g) & 1u) && flag[g] == 0) {
                     donemask |= 1u << g;
                     et_mask |= 1u << g;
                     if (tid == g) my_iters = it;
                 }
+            if (tid < kMaxG) s_flag[(it + 1) & 1][tid] = 0;
+            if (donemask == fullmask) break;
         }
-        if (tid < kMaxG) s_flag[(it + 1) & 1][tid] = 0;
-        if (donemask == fullmask) break;
         // ---- variable-node pass
-        for (int t = warp; t < c.ncore * ncolumns; t += NW) {
-            const int j = c.vn_order[t / ncolumns];
-            const Lane L = lane_of(c, a, t % ncolumns, lane, donemask);
-            vn_col(c, a, smem + L.g * a.slot_bytes, j, L);
-        }
+        const bool active2 = me.valid && !((donemask >> me.g) & 1u);
+        if (__any_sync(0xffffffffu, active2))
+            for (int o = sub; o < T.ncore; o += T.S) vn_col(T, me, T.vn_order[o], active2);
         __syncthreads();
     }
 
     // ---- final decision + syndrome for the codeblocks that did not leave early
     uint32_t okmask = et_mask;
     if (donemask != fullmask) {
-        int *flag = s_flag[it & 1];  // cleared above, not yet written
-        for (int t = warp; t < c.nrows * ncolumns; t += NW) {
-            const int i = t / ncolumns;
-            const Lane L = lane_of(c, a, t % ncolumns, lane, donemask);
-            final_row(c, a, smem + L.g * a.slot_bytes, i, L, flag);
-        }
+        int *flag = s_flag[it & 1];  // cleared, not yet written
+        const bool active = me.valid && !((donemask >> me.g) & 1u);
+        for (int o = sub; o < T.nrows; o += T.S) syndrome_row<true>(T, me, o, active, flag);
         __syncthreads();
         for (int g = 0; g < G; ++g)
             if (!((donemask >> g) & 1u) && flag[g] == 0) okmask |= 1u << g;
@@ -298,35 +328,36 @@ decode_minsum_kernel(const __grid_constant__ QcCfg c, const __grid_constant__ De
         if (a.status) a.status[cb0 + tid] = (okmask >> tid) & 1u;
         if (a.iters) a.iters[cb0 + tid] = my_iters;
     }
+    const int NW = NT >> 5;
     for (int g = 0; g < G; ++g) {
         const int cb = cb0 + g;
         if (cb >= a.B) break;
-        const char *slot = smem + g * a.slot_bytes;
+        const char *slot = smem + g * T.slot_bytes;
         const float *LQ = reinterpret_cast<const float *>(slot);
-        const uint32_t *ext = reinterpret_cast<const uint32_t *>(slot + a.off_ext);
+        const uint32_t *ext = reinterpret_cast<const uint32_t *>(slot + T.off_ext);
         const bool et = (et_mask >> g) & 1u;
-        const int sub = (g % c.per) << c.lanes_log2;
+        const int subpos = (g % T.per) << T.lanes_log2;
         if (a.ck) {
-            int8_t *out = a.ck + (size_t)cb * c.Nfull;
-            const int ncoreN = c.ncore * Zc;
-            for (int n = tid; n < c.Nfull; n += NT) {
+            int8_t *out = a.ck + (size_t)cb * T.Nfull;
+            const int ncoreN = T.ncore * Zc;
+            for (int n = tid; n < T.Nfull; n += NT) {
                 int bit;
                 if (n < ncoreN) {
                     const float x = LQ[n];
                     bit = et ? (x < 0.f) : (x <= 0.f);
                 } else {
                     const int m = n - ncoreN, i4 = m / Zc, r = m - i4 * Zc;
-                    bit = (ext[i4 * c.tiles + (r >> 5)] >> (sub + (r & 31))) & 1u;
+                    bit = (ext[i4 * T.tiles + (r >> 5)] >> (subpos + (r & 31))) & 1u;
                 }
                 out[n] = (int8_t)bit;
             }
         }
         if (a.info) {
-            const int nwords = (c.K + 31) / 32;
-            for (int w = warp; w < nwords; w += NW) {
+            const int nwords = (T.K + 31) / 32;
+            for (int w = (tid >> 5); w < nwords; w += NW) {
                 const int n = 32 * w + lane;
                 bool bit = false;
-                if (n < c.K) { const float x = LQ[n]; bit = et ? (x < 0.f) : (x <= 0.f); }
+                if (n < T.K) { const float x = LQ[n]; bit = et ? (x < 0.f) : (x <= 0.f); }
                 const uint32_t word = __ballot_sync(0xffffffffu, bit);
                 if (lane == 0) a.info[(size_t)cb * nwords + w] = word;
             }
@@ -334,37 +365,117 @@ decode_minsum_kernel(const __grid_constant__ QcCfg c, const __grid_constant__ De
     }
 }
 
-void fill_layout(const QcCfg &cfg, DecArgs *a)
+constexpr int kSmemMax = 227 * 1024 - 512;  // 227 KB per CTA minus the static flags
+
+// Host: derive the kernel tables and launch geometry for one (bgn, Zc).
+int build_dec_tab(const QcCfg &c, DecTab *T)
 {
-    const int Zc = cfg.Zc;
-    a->off_mags = cfg.ncore * Zc * 4;
-    a->off_mags = (a->off_mags + 7) & ~7;
-    a->off_bits = a->off_mags + cfg.nrows * Zc * 8;
-    a->off_ext = (a->off_bits + cfg.bits_bytes_per_zc * Zc + 3) & ~3;
-    a->slot_bytes = (a->off_ext + (cfg.nrows - 4) * cfg.tiles * 4 + 15) & ~15;
+    std::memset(T, 0, sizeof(*T));
+    const int Zc = c.Zc;
+    T->Zc = Zc; T->Z4 = 4 * Zc; T->Z8 = 8 * Zc;
+    T->nrows = c.nrows; T->ncore = c.ncore; T->kb = c.kb; T->K = c.K; T->N = c.N; T->Nfull = c.Nfull;
+    T->tiles = c.tiles; T->lanes = c.lanes; T->lanes_log2 = c.lanes_log2; T->per = c.per;
+    // slot layout
+    T->off_mags = (c.ncore * Zc * 4 + 7) & ~7;
+    T->off_bits = T->off_mags + c.nrows * Zc * 8;
+    T->off_ext = (T->off_bits + c.bits_bytes_per_zc * Zc + 3) & ~3;
+    T->slot_bytes = (T->off_ext + (c.nrows - 4) * c.tiles * 4 + 15) & ~15;
+    // geometry: as many codeblocks per CTA as fit, at most 16 warp columns and 32 codeblocks
+    int gmax = kSmemMax / T->slot_bytes;
+    if (gmax < 1) return NRLDPC_EINVAL;
+    gmax = std::min(gmax, kMaxG);
+    int G = std::min(gmax, std::max(1, 16 / c.tiles) * c.per);
+    if (c.per > 1) G = std::max(c.per, (G / c.per) * c.per);
+    if (G > gmax) return NRLDPC_EINVAL;
+    T->G = G;
+    T->ncolumns = (G / c.per) * c.tiles;
+    T->S = std::max(1, 32 / T->ncolumns);
+    T->nwarps = T->ncolumns * T->S;
+    if (T->nwarps > 32) return NRLDPC_EINVAL;
+
+    for (int i = 0; i < c.nrows; ++i) {
+        RowInfo &r = T->row[i];
+        r.mag_off = T->off_mags + i * Zc * 8;
+        r.bits_off = T->off_bits + c.bits_off[i] * Zc;
+        r.ext_llr = (i >= 4) ? (uint32_t)(c.kb + i - 2) * Zc : 0;
+        r.e0 = c.rowptr[i];
+        r.deg = (uint8_t)(c.rowptr[i + 1] - c.rowptr[i]);
+        r.wide = c.wide[i];
+        const bool okdeg = (i < 4) ? (r.deg == 19 || r.deg == 10 || r.deg == 8) : (r.deg >= 3 && r.deg <= 10);
+        if (!okdeg || (r.wide != (r.deg == 19))) return NRLDPC_EINVAL;
+    }
+    for (int e = 0; e < c.rowptr[c.nrows]; ++e) {
+        const int j = c.edge[e] & 0xff, P = c.edge[e] >> 8;
+        T->cn_edge[e] = make_uint2((uint32_t)(j < c.ncore ? j * Zc * 4 : 0), (uint32_t)P * 4);
+    }
+    for (int j = 0; j < c.ncore; ++j) {
+        ColInfo &ci = T->col[j];
+        ci.lq_off = j * Zc * 4;
+        ci.llr_off = j >= 2 ? (uint32_t)(j - 2) * Zc : kNoLlr;
+        ci.q0 = c.colptr[j];
+        ci.deg = (uint8_t)(c.colptr[j + 1] - c.colptr[j]);
+        int nwide = 0;
+        for (int q = c.colptr[j]; q < c.colptr[j + 1]; ++q) {
+            const uint32_t en = c.centry[q];
+            const int i = en & 63, k = (en >> 6) & 31, bitpos = (en >> 11) & 31, back = en >> 16;
+            const bool wide = c.wide[i];
+            if (wide) { if (nwide != q - c.colptr[j]) return NRLDPC_EINVAL; ++nwide; }  // wide rows must lead
+            T->vn_entry[q] = make_uint4(T->row[i].mag_off, T->row[i].bits_off, (uint32_t)back * 8,
+                                        ((uint32_t)k << (wide ? 24 : 12)) | (uint32_t)(31 - bitpos));
+        }
+        ci.nwide = (uint8_t)nwide;
+    }
+    // balanced static split: rank by degree, deal to the S warp groups in snake order
+    auto deal = [&](int n, auto degree, uint8_t *order) {
+        std::vector<int> idx(n);
+        for (int i = 0; i < n; ++i) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return degree(x) > degree(y); });
+        const int S = T->S;
+        std::vector<std::vector<int>> grp(S);
+        for (int p = 0; p < n; ++p) {
+            const int round = p / S, pos = p % S;
+            const bool partial = (round + 1) * S > n;  // the last, incomplete round fills groups 0..rem-1
+            grp[((round & 1) && !partial) ? S - 1 - pos : pos].push_back(idx[p]);
+        }
+        // order[o] for o = s, s+S, ... must enumerate group s
+        std::vector<int> out(n, -1);
+        for (int s = 0; s < S; ++s)
+            for (size_t t = 0; t < grp[s].size(); ++t)
+                if ((int)(s + t * S) < n) out[s + t * S] = grp[s][t];
+        for (int o = 0; o < n; ++o) {
+            if (out[o] < 0) return false;
+            order[o] = (uint8_t)out[o];
+        }
+        return true;
+    };
+    if (!deal(c.nrows, [&](int i) { return (int)T->row[i].deg; }, T->cn_order)) return NRLDPC_EINVAL;
+    if (!deal(c.ncore, [&](int j) { return (int)T->col[j].deg; }, T->vn_order)) return NRLDPC_EINVAL;
+    return NRLDPC_OK;
 }
 
-constexpr int kSmemMax = 227 * 1024;
+const DecTab *get_dec_tab(const QcCfg &cfg)
+{
+    static std::mutex mu;
+    static std::map<int, DecTab *> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    const int key = cfg.bgn * 1024 + cfg.Zc;
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    DecTab *T = new DecTab;
+    if (build_dec_tab(cfg, T) != NRLDPC_OK) { delete T; return nullptr; }
+    cache[key] = T;
+    return T;
+}
 
 }  // namespace
 
 int decode_minsum_geometry(const QcCfg &cfg, int *G_out, int *threads, int *smem)
 {
-    DecArgs a;
-    fill_layout(cfg, &a);
-    int gmax = kSmemMax / a.slot_bytes;
-    if (gmax < 1) return NRLDPC_EINVAL;
-    if (gmax > kMaxG) gmax = kMaxG;
-    // aim for ~12 warp-tile columns per CTA (what one Zc=384 codeblock provides)
-    int want = ((12 + cfg.tiles - 1) / cfg.tiles) * cfg.per;
-    int G = want < gmax ? want : gmax;
-    if (cfg.per > 1) G = (G / cfg.per) * cfg.per;
-    if (G < 1) G = 1;
-    const int columns = (G / cfg.per) * cfg.tiles;
-    int nt = columns >= 8 ? 1024 : (columns >= 4 ? 512 : 256);
-    if (G_out) *G_out = G;
-    if (threads) *threads = nt;
-    if (smem) *smem = G * a.slot_bytes;
+    const DecTab *T = get_dec_tab(cfg);
+    if (!T) return NRLDPC_EINVAL;
+    if (G_out) *G_out = T->G;
+    if (threads) *threads = T->nwarps * 32;
+    if (smem) *smem = T->G * T->slot_bytes;
     return NRLDPC_OK;
 }
 
@@ -373,22 +484,20 @@ int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_it
                          cudaStream_t s)
 {
     if (B <= 0) return NRLDPC_OK;
+    const DecTab *T = get_dec_tab(cfg);
+    if (!T) { set_error("decode_minsum: no kernel geometry for bgn=%d Zc=%d", cfg.bgn, cfg.Zc); return NRLDPC_EINVAL; }
     DecArgs a;
-    fill_layout(cfg, &a);
-    int G, nt, smem;
-    if (decode_minsum_geometry(cfg, &G, &nt, &smem)) { set_error("decode_minsum: codeblock does not fit in shared memory"); return NRLDPC_EINVAL; }
-    a.llr = d_llr; a.B = B; a.G = G; a.max_iter = max_iter; a.early_term = early_term;
-    a.alpha = alpha; a.beta = beta; a.ck = d_ck; a.info = d_info; a.status = d_status; a.iters = d_iters;
-    const int grid = (B + G - 1) / G;
+    a.llr = d_llr; a.B = B; a.max_iter = max_iter; a.alpha = alpha; a.beta = beta;
+    a.ck = d_ck; a.info = d_info; a.status = d_status; a.iters = d_iters;
+    const int grid = (B + T->G - 1) / T->G, nt = T->nwarps * 32, smem = T->G * T->slot_bytes;
     auto launch = [&](auto kern) -> int {
-        NRLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        kern<<<grid, nt, smem, s>>>(cfg, a);
+        NRLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, nt, smem, s>>>(*T, a);
         NRLDPC_CUDA(cudaGetLastError());
         return NRLDPC_OK;
     };
-    if (nt == 1024) return launch(decode_minsum_kernel<1024>);
-    if (nt == 512) return launch(decode_minsum_kernel<512>);
-    return launch(decode_minsum_kernel<256>);
+    if (nt <= 768) return early_term ? launch(decode_minsum_kernel<768, true>) : launch(decode_minsum_kernel<768, false>);
+    return early_term ? launch(decode_minsum_kernel<1024, true>) : launch(decode_minsum_kernel<1024, false>);
 }
 
 }  // namespace nrldpc

@@ -91,24 +91,36 @@ def test_encode_parity_check_property_headline(eng):
 
 # ------------------------------------------------------------------ min-sum decoder
 
-def test_decode_golden_fp32(eng, dec_golden):
-    """fp32 hot kernel vs the reference's float64 outputs on the committed vectors."""
-    bad = []
-    n = 0
+def test_decode_golden_fp32(eng, oracle, dec_golden):
+    """fp32 hot kernel on the committed vectors of the live reference (float64 arithmetic).
+
+    Bar (north_star): identical hard bits, status and iteration count on >= 99.99% of codeblocks at
+    operating points.  On these 114 vectors: every CONVERGED block must match bit for bit; status and
+    iteration counts must match on all; a non-converged block may differ in a few bits because fp32
+    and fp64 round differently (1 vector, BG2 Zc=208 seed 1123, 1 bit -- the fp32 CPU restatement of
+    the reference shows the same bit).  The kernel itself must equal the fp32 restatement exactly."""
+    bad, n = [], 0
     for g in dec_golden:
         if g["algo"] != "min-sum":
             continue
         r = eng.decode_batch(g["llr"][None, :], g["Zc"], g["bgn"], g["L"], g["alpha"], g["beta"], True)
-        ok = np.array_equal(r["ck"][0], g["ck"]) and bool(r["status"][0]) == g["status"] and int(r["iters"][0]) == g["iters"]
+        tag = (g["bgn"], g["Zc"], g["seed"])
+        assert bool(r["status"][0]) == g["status"] and int(r["iters"][0]) == g["iters"], tag
+        c32, s32, i32 = oracle.decode_batch(g["llr"][None, :], g["Zc"], g["bgn"], g["L"], "min-sum", g["alpha"], g["beta"], 1, np.float32)
+        assert np.array_equal(r["ck"], c32) and bool(s32[0]) == g["status"] and int(i32[0]) == g["iters"], tag
+        nd = int((r["ck"][0] != g["ck"]).sum())
+        if g["status"]:
+            assert nd == 0, tag
+        elif nd:
+            bad.append(tag + (nd,))
         n += 1
-        if not ok:
-            bad.append((g["bgn"], g["Zc"], g["seed"], int((r["ck"][0] != g["ck"]).sum()), int(r["iters"][0]), g["iters"]))
-    assert n >= 100 and not bad, bad
+    assert n >= 100
+    assert len(bad) <= 1 and all(b[3] <= 2 for b in bad), bad
 
 
 def test_decode_golden_fp64_exact(eng, dec_golden):
     for g in dec_golden:
-        if g["algo"] != "min-sum" or g["Zc"] > 128:
+        if g["algo"] != "min-sum":
             continue
         ck, st, it = eng.decode_ref_batch(g["llr"][None, :].astype(np.float64), g["Zc"], g["bgn"], g["L"], "min-sum",
                                           g["alpha"], g["beta"], True, f64=True)
