@@ -226,7 +226,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": Be * ((K_INFO + 31) // 32 * 4 + 1 + 4), "codeblocks_per_step": Be},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                         "traffic": TRAFFIC_BYTES_PER_CB * B, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_CB,
                          "kernel": "decode_minsum_kernel", "kernel_ms": ms / args.steps,
                          "note": "HBM is not the binding roof of this kernel (10 on-chip iterations per byte); "
@@ -248,8 +248,9 @@ def ctypes_int():
     return ctypes.c_int()
 
 
-# dram bytes (read+write) per decode launch from the committed `ncu --set full` capture, or None
-TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum per codeblock from the committed `ncu --set full` capture
+# (profiles/r1_decode_minsum_ncu_summary.md: 60.07 MB + 0.38 MB for 592 codeblocks)
+TRAFFIC_BYTES_PER_CB = (60069376 + 384000) / 592
 
 
 def main():

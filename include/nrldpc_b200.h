@@ -122,6 +122,13 @@ int nrldpc_decode_bf_host(const double *llr, int B, int bgn, int Zc, int max_ite
  */
 int nrldpc_awgn_llr(const int8_t *d_dn, long long count, float snr_db, unsigned long long seed,
                     unsigned long long offset, float *d_llr, void *stream);
+/* Row form: row j of [rows, cols] draws from the counter range of id = first_id + j*id_stride, so a
+ * codeblock's noise depends only on its global id -- any sharding of a Monte-Carlo point over GPUs
+ * sees the same codeblocks. */
+int nrldpc_awgn_llr_rows(const int8_t *d_dn, long long rows, long long cols, float snr_db, unsigned long long seed,
+                         long long first_id, long long id_stride, float *d_llr, void *stream);
+int nrldpc_random_bits_rows(int8_t *d_bits, long long rows, long long cols, unsigned long long seed,
+                            long long first_id, long long id_stride, void *stream);
 /* Uniform random bits (Philox), int8 0/1. */
 int nrldpc_random_bits(int8_t *d_bits, long long count, unsigned long long seed, unsigned long long offset,
                        void *stream);

@@ -50,6 +50,8 @@ def _declare(L):
         "nrldpc_decode_bf_host": (i, [p, i, i, i, i, p, p, p]),
         "nrldpc_awgn_llr": (i, [p, ll, f, ull, ull, p, p]),
         "nrldpc_random_bits": (i, [p, ll, ull, ull, p]),
+        "nrldpc_awgn_llr_rows": (i, [p, ll, ll, f, ull, ll, ll, p, p]),
+        "nrldpc_random_bits_rows": (i, [p, ll, ll, ull, ll, ll, p]),
         "nrldpc_count_errors": (i, [p, ll, p, ll, i, i, p, p, p]),
         "nrldpc_crc_encode": (i, [p, i, i, i, p, p]),
         "nrldpc_crc_check": (i, [p, i, i, i, p, p]),

@@ -243,7 +243,29 @@ int nrldpc_decode_minsum_geometry(int bgn, int Zc, int *cbs_per_cta, int *thread
 }
 
 // Host-buffer entry point: double-buffered chunks so that (with pinned host memory) the H2D copy of
-// chunk i+1 and the D2H copy of chunk i-1 overlap the decode of chunk i.
+// chunk i+1 and the D2H copy of chunk i-1 overlap the decode of chunk i.  The two stages' device
+// buffers and streams are created once per device and reused (grow-only) by later calls.
+namespace {
+struct HostStage {
+    void *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // llr, ck, info, status, iters
+    size_t cap[5] = {0, 0, 0, 0, 0};
+    cudaStream_t s = nullptr;
+    int ensure(int which, size_t bytes)
+    {
+        if (bytes <= cap[which]) return NRLDPC_OK;
+        if (buf[which]) { NRLDPC_CUDA(cudaFree(buf[which])); buf[which] = nullptr; cap[which] = 0; }
+        NRLDPC_CUDA(cudaMalloc(&buf[which], bytes));
+        cap[which] = bytes;
+        return NRLDPC_OK;
+    }
+};
+struct HostPipe {
+    std::mutex mu;
+    std::map<int, std::pair<HostStage, HostStage>> per_device;
+};
+HostPipe g_pipe;
+}  // namespace
+
 int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
                               int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters)
 {
@@ -251,39 +273,39 @@ int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_
     if (!c) return NRLDPC_EINVAL;
     if (B < 0 || max_iter < 0 || !llr) { set_error("decode_minsum: bad argument"); return NRLDPC_EINVAL; }
     if (B == 0) return NRLDPC_OK;
+    int dev = 0;
+    NRLDPC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_pipe.mu);
+    auto &pair = g_pipe.per_device[dev];
+    HostStage *st[2] = {&pair.first, &pair.second};
     const size_t llr_bytes = (size_t)c->N * 4, nwords = (size_t)(c->K + 31) / 32;
-    int chunk = (int)std::max<size_t>(1, ((size_t)192 << 20) / llr_bytes);
-    if (chunk > B) chunk = B;
-    struct Stage {
-        DevBuf llr, ck, info, st, it;
-        cudaStream_t s = nullptr;
-        ~Stage() { if (s) cudaStreamDestroy(s); }
-    } st[2];
+    int chunk = (int)std::max<size_t>(1, ((size_t)128 << 20) / llr_bytes);
+    if (chunk > B) chunk = (B + 1) / 2 > 256 ? (B + 1) / 2 : B;  // two chunks still overlap copy and compute
     const int nstage = B > chunk ? 2 : 1;
     for (int i = 0; i < nstage; ++i) {
-        NRLDPC_CUDA(cudaStreamCreateWithFlags(&st[i].s, cudaStreamNonBlocking));
-        NRLDPC_CUDA(st[i].llr.alloc((size_t)chunk * llr_bytes));
-        if (ck) NRLDPC_CUDA(st[i].ck.alloc((size_t)chunk * c->Nfull));
-        if (info_packed) NRLDPC_CUDA(st[i].info.alloc((size_t)chunk * nwords * 4));
-        NRLDPC_CUDA(st[i].st.alloc((size_t)chunk));
-        NRLDPC_CUDA(st[i].it.alloc((size_t)chunk * 4));
+        if (!st[i]->s) NRLDPC_CUDA(cudaStreamCreateWithFlags(&st[i]->s, cudaStreamNonBlocking));
+        if (int rc = st[i]->ensure(0, (size_t)chunk * llr_bytes)) return rc;
+        if (ck) if (int rc = st[i]->ensure(1, (size_t)chunk * c->Nfull)) return rc;
+        if (info_packed) if (int rc = st[i]->ensure(2, (size_t)chunk * nwords * 4)) return rc;
+        if (int rc = st[i]->ensure(3, (size_t)chunk)) return rc;
+        if (int rc = st[i]->ensure(4, (size_t)chunk * 4)) return rc;
     }
     int k = 0;
     for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
-        Stage &S = st[k % nstage];
+        HostStage &S = *st[k % nstage];
         const int nb = std::min(chunk, B - b0);
-        NRLDPC_CUDA(cudaMemcpyAsync(S.llr.p, llr + (size_t)b0 * c->N, (size_t)nb * llr_bytes, cudaMemcpyHostToDevice, S.s));
-        if (int rc = launch_decode_minsum(*c, S.llr.as<float>(), nb, max_iter, alpha, beta, early_term,
-                                          ck ? S.ck.as<int8_t>() : nullptr, info_packed ? S.info.as<uint32_t>() : nullptr,
-                                          S.st.as<uint8_t>(), S.it.as<int32_t>(), S.s))
+        NRLDPC_CUDA(cudaMemcpyAsync(S.buf[0], llr + (size_t)b0 * c->N, (size_t)nb * llr_bytes, cudaMemcpyHostToDevice, S.s));
+        if (int rc = launch_decode_minsum(*c, (const float *)S.buf[0], nb, max_iter, alpha, beta, early_term,
+                                          ck ? (int8_t *)S.buf[1] : nullptr, info_packed ? (uint32_t *)S.buf[2] : nullptr,
+                                          (uint8_t *)S.buf[3], (int32_t *)S.buf[4], S.s))
             return rc;
-        if (ck) NRLDPC_CUDA(cudaMemcpyAsync(ck + (size_t)b0 * c->Nfull, S.ck.p, (size_t)nb * c->Nfull, cudaMemcpyDeviceToHost, S.s));
+        if (ck) NRLDPC_CUDA(cudaMemcpyAsync(ck + (size_t)b0 * c->Nfull, S.buf[1], (size_t)nb * c->Nfull, cudaMemcpyDeviceToHost, S.s));
         if (info_packed)
-            NRLDPC_CUDA(cudaMemcpyAsync(info_packed + (size_t)b0 * nwords, S.info.p, (size_t)nb * nwords * 4, cudaMemcpyDeviceToHost, S.s));
-        if (status) NRLDPC_CUDA(cudaMemcpyAsync(status + b0, S.st.p, (size_t)nb, cudaMemcpyDeviceToHost, S.s));
-        if (iters) NRLDPC_CUDA(cudaMemcpyAsync(iters + b0, S.it.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, S.s));
+            NRLDPC_CUDA(cudaMemcpyAsync(info_packed + (size_t)b0 * nwords, S.buf[2], (size_t)nb * nwords * 4, cudaMemcpyDeviceToHost, S.s));
+        if (status) NRLDPC_CUDA(cudaMemcpyAsync(status + b0, S.buf[3], (size_t)nb, cudaMemcpyDeviceToHost, S.s));
+        if (iters) NRLDPC_CUDA(cudaMemcpyAsync(iters + b0, S.buf[4], (size_t)nb * 4, cudaMemcpyDeviceToHost, S.s));
     }
-    for (int i = 0; i < nstage; ++i) NRLDPC_CUDA(cudaStreamSynchronize(st[i].s));
+    for (int i = 0; i < nstage; ++i) NRLDPC_CUDA(cudaStreamSynchronize(st[i]->s));
     return NRLDPC_OK;
 }
 

@@ -29,26 +29,32 @@ __device__ __forceinline__ uint4 philox_at(unsigned long long seed, unsigned lon
                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
-__global__ void random_bits_kernel(int8_t *bits, long long count, unsigned long long seed, unsigned long long offset)
+// rows x cols outputs; row j uses the Philox counters (first_id + j*id_stride) * bpr + blk (+ ctr0), so a
+// codeblock's random stream depends only on its global id, not on how the batch is sharded.
+__global__ void random_bits_kernel(int8_t *bits, long long rows, long long cols, unsigned long long seed,
+                                   unsigned long long ctr0, long long first_id, long long id_stride)
 {
-    // one Philox block = 128 bits -> 128 outputs
-    const long long nblk = (count + 127) / 128;
-    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
-        const uint4 x = philox_at(seed, offset + (unsigned long long)b);
+    const long long bpr = (cols + 127) / 128, nblk = rows * bpr;  // one Philox block = 128 bits
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nblk; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / bpr, blk = t - row * bpr;
+        const uint4 x = philox_at(seed, ctr0 + (unsigned long long)((first_id + row * id_stride) * bpr + blk));
         const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-        const long long base = b * 128;
+        const long long base = blk * 128;
+        int8_t *out = bits + row * cols;
 #pragma unroll
         for (int i = 0; i < 128; ++i)
-            if (base + i < count) bits[base + i] = (int8_t)((w[i >> 5] >> (i & 31)) & 1u);
+            if (base + i < cols) out[base + i] = (int8_t)((w[i >> 5] >> (i & 31)) & 1u);
     }
 }
 
-__global__ void awgn_llr_kernel(const int8_t *__restrict__ dn, long long count, float sigma, float scale,
-                                unsigned long long seed, unsigned long long offset, float *__restrict__ llr)
+__global__ void awgn_llr_kernel(const int8_t *__restrict__ dn, long long rows, long long cols, float sigma, float scale,
+                                unsigned long long seed, unsigned long long ctr0, long long first_id, long long id_stride,
+                                float *__restrict__ llr)
 {
-    const long long nblk = (count + 3) / 4;
-    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
-        const uint4 x = philox_at(seed ^ 0x9E3779B97F4A7C15ull, offset + (unsigned long long)b);
+    const long long bpr = (cols + 3) / 4, nblk = rows * bpr;  // one Philox block = 4 normals
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nblk; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / bpr, blk = t - row * bpr;
+        const uint4 x = philox_at(seed ^ 0x9E3779B97F4A7C15ull, ctr0 + (unsigned long long)((first_id + row * id_stride) * bpr + blk));
         // Box-Muller on two uniform pairs
         const float u0 = ((x.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((x.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
         const float u2 = ((x.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((x.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
@@ -57,13 +63,13 @@ __global__ void awgn_llr_kernel(const int8_t *__restrict__ dn, long long count, 
         sincospif(2.0f * u1, &s0, &c0);
         sincospif(2.0f * u3, &s1, &c1);
         const float n[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
-        const long long base = b * 4;
+        const long long base = blk * 4;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (base + i < count) {
-                const int d = dn[base + i];
+            if (base + i < cols) {
+                const int d = dn[row * cols + base + i];
                 // :252-257  en = 1 - 2 dn ; fn = en + N(0, sigma) ; LLR = 2 fn / sigma^2
-                llr[base + i] = d < 0 ? 0.0f : scale * ((1.0f - 2.0f * (float)d) + sigma * n[i]);
+                llr[row * cols + base + i] = d < 0 ? 0.0f : scale * ((1.0f - 2.0f * (float)d) + sigma * n[i]);
             }
     }
 }
@@ -127,13 +133,37 @@ __global__ void crc_kernel(const int8_t *__restrict__ in, int B, int A, int L, u
 
 using namespace nrldpc;
 
+static int grid_for(long long nblk, int per_sm)
+{
+    const long long g = (nblk + 255) / 256;
+    return (int)(g > 148LL * per_sm ? 148LL * per_sm : (g < 1 ? 1 : g));
+}
+
+extern "C" int nrldpc_random_bits_rows(int8_t *d_bits, long long rows, long long cols, unsigned long long seed,
+                                       long long first_id, long long id_stride, void *stream)
+{
+    if (rows <= 0 || cols <= 0) return NRLDPC_OK;
+    random_bits_kernel<<<grid_for(rows * ((cols + 127) / 128), 16), 256, 0, (cudaStream_t)stream>>>(d_bits, rows, cols, seed, 0, first_id, id_stride);
+    NRLDPC_CUDA(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
 extern "C" int nrldpc_random_bits(int8_t *d_bits, long long count, unsigned long long seed, unsigned long long offset,
                                   void *stream)
 {
     if (count <= 0) return NRLDPC_OK;
-    const long long nblk = (count + 127) / 128;
-    const int grid = (int)((nblk + 255) / 256 > 148 * 16 ? 148 * 16 : (nblk + 255) / 256);
-    random_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_bits, count, seed, offset);
+    random_bits_kernel<<<grid_for((count + 127) / 128, 16), 256, 0, (cudaStream_t)stream>>>(d_bits, 1, count, seed, offset, 0, 0);
+    NRLDPC_CUDA(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_awgn_llr_rows(const int8_t *d_dn, long long rows, long long cols, float snr_db, unsigned long long seed,
+                                    long long first_id, long long id_stride, float *d_llr, void *stream)
+{
+    if (rows <= 0 || cols <= 0) return NRLDPC_OK;
+    const double sigma = pow(10.0, -(double)snr_db / 20.0), np = pow(10.0, -(double)snr_db / 10.0);
+    awgn_llr_kernel<<<grid_for(rows * ((cols + 3) / 4), 32), 256, 0, (cudaStream_t)stream>>>(
+        d_dn, rows, cols, (float)sigma, (float)(2.0 / np), seed, 0, first_id, id_stride, d_llr);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
 }
@@ -143,9 +173,8 @@ extern "C" int nrldpc_awgn_llr(const int8_t *d_dn, long long count, float snr_db
 {
     if (count <= 0) return NRLDPC_OK;
     const double sigma = pow(10.0, -(double)snr_db / 20.0), np = pow(10.0, -(double)snr_db / 10.0);
-    const long long nblk = (count + 3) / 4;
-    const int grid = (int)((nblk + 255) / 256 > 148 * 32 ? 148 * 32 : (nblk + 255) / 256);
-    awgn_llr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_dn, count, (float)sigma, (float)(2.0 / np), seed, offset, d_llr);
+    awgn_llr_kernel<<<grid_for((count + 3) / 4, 32), 256, 0, (cudaStream_t)stream>>>(
+        d_dn, 1, count, (float)sigma, (float)(2.0 / np), seed, offset, 0, 0, d_llr);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
 }

@@ -1,0 +1,202 @@
+"""Batched Monte-Carlo driver: the drop-in for scripts/internal/sim_ldpc_internal.run_ldpc_simulation.
+
+The reference loop decodes ONE codeblock per pass (scripts/internal/sim_ldpc_internal.py:49-77) and only
+looks at its stopping rule when test_count is 1000, 2000, 4000 or 10000 (:67-77).  Here every stretch
+between two such checkpoints is generated, encoded and decoded as one batch on the GPU, so the rule,
+the BLER values and the pickle layout ([sim_config, test_config_list, test_results_list], :87-91) are
+those of the reference.
+
+Sharding: codeblocks are independent.  With torch.distributed initialised, rank k of W
+takes every W-th codeblock of a batch and the only collective is an all-reduce(SUM) of two int64
+counters per checkpoint.
+
+Input generation
+  rng="numpy"  (default) the reference's own draws from NumPy's global RNG, in its order (randint
+               :247 then normal :253 per codeblock), so np.random.seed(s) reproduces the reference's
+               inputs bit for bit; every rank draws the full stream and keeps its share.
+  rng="device" Philox bits + noise generated on the GPU (nrldpc_random_bits / nrldpc_awgn_llr) for
+               10^6-codeblock points; statistically equivalent, not seed-compatible.
+"""
+import pickle
+import time
+
+import numpy as np
+
+CHECKPOINTS = (1000, 2000, 4000, 10000)   # np.array([200,400,800,2000])*5, sim_ldpc_internal.py:67
+FAIL_LIMITS = (50, 25, 10)                # np.array([10,5,2])*5, :68
+
+
+def test_plan(algo_list, alpha_list, beta_list, mixed_list, L_list):
+    """[(flag, algo, L, alpha, beta)] in the reference's nesting order (sim_ldpc_internal.py:15-40)."""
+    plan = []
+    for algo in algo_list:
+        if algo in ['BP', 'BF', 'min-sum']:
+            params = [(1, 0)]
+        elif algo == 'NMS':
+            params = [(a, 0) for a in alpha_list]
+        elif algo == 'OMS':
+            params = [(1, b) for b in beta_list]
+        else:
+            params = [(m[0], m[1]) for m in mixed_list]
+        for L in L_list:
+            for (a, b) in params:
+                if algo in ['BF', 'BP', 'min-sum']:
+                    flag = '{} L={}'.format(algo, L)
+                elif algo == 'NMS':
+                    flag = 'NMS-alpha={}-L={}'.format(a, L)
+                elif algo == 'OMS':
+                    flag = 'OMS-beta={}-L={}'.format(b, L)
+                else:
+                    flag = 'mixed-MS-[alpha,beta]=[{},{}]-L={}'.format(a, b, L)
+                plan.append((flag, algo, L, a, b))
+    return plan
+
+
+def stop_now(test_count, failed_count):
+    """The reference's termination check (sim_ldpc_internal.py:69-77)."""
+    for cp, lim in zip(CHECKPOINTS[:3], FAIL_LIMITS):
+        if test_count == cp and failed_count >= lim:
+            return True
+    return test_count == CHECKPOINTS[3]
+
+
+class _Dist:
+    def __init__(self):
+        self.rank, self.world, self.dist = 0, 1, None
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.rank, self.world, self.dist = dist.get_rank(), dist.get_world_size(), dist
+        except ImportError:
+            pass
+
+    def sum(self, values, device=None):
+        if self.world == 1:
+            return [int(v) for v in values]
+        import torch
+        t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
+        self.dist.all_reduce(t)
+        return t.tolist()
+
+
+class CudaBackend:
+    """generate / encode / decode one batch share on the GPU through the C ABI."""
+
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device if device is not None else "cuda")
+        self.reduce_device = self.device
+
+    def numpy_batch(self, Zc, bgn, snr_db, crcpoly, n, take):
+        """n codeblocks drawn exactly like for_test_5g_ldpc_encoder (nr_ldpc_decode.py:247-257); only the
+        ones in `take` are encoded.  Returns (blkandcrc int8[m,K], llr float64[m,N])."""
+        from . import crc, engine
+        K, N = ((22, 66) if bgn == 1 else (10, 50))
+        K, N = K * Zc, N * Zc
+        crc_len = 24 if crcpoly in ['24A', '24B'] else 16
+        sigma = 10 ** (-snr_db / 20)
+        bits = np.empty((len(take), K - crc_len), np.int8)
+        noise = np.empty((len(take), N))
+        want = {b: i for i, b in enumerate(take)}
+        for b in range(n):  # the global stream must advance for every codeblock, kept or not
+            inb = np.random.randint(2, size=K - crc_len)
+            nz = np.random.normal(0, sigma, N)
+            if b in want:
+                bits[want[b]] = inb
+                noise[want[b]] = nz
+        if not len(take):
+            return np.empty((0, K), np.int8), np.empty((0, N))
+        blk = crc.nr_crc_encode_batch(bits, crcpoly)
+        dn = engine.encode_batch(blk.copy(), bgn, Zc)
+        llr = 2 * ((1 - 2 * dn) + noise) / 10 ** (-snr_db / 10)
+        return blk, llr
+
+    def count_failures(self, Zc, bgn, snr_db, crcpoly, algo, L, alpha, beta, n, take, rng, seed, offset):
+        from . import engine, _lib
+        import ctypes
+        torch = self.torch
+        K = (22 if bgn == 1 else 10) * Zc
+        if not len(take) and rng != "numpy":
+            return 0
+        if rng == "numpy":
+            blk, llr = self.numpy_batch(Zc, bgn, snr_db, crcpoly, n, take)
+            if not len(take):
+                return 0
+            if algo == 'BF':
+                ck, _, _ = engine.decode_bf_batch(llr, Zc, bgn, L)
+            elif algo == 'BP':
+                ck, _, _ = engine.decode_ref_batch(llr, Zc, bgn, L, 'BP', 1, 0, True, f64=True)
+            else:
+                ck = engine.decode_batch(llr.astype(np.float32), Zc, bgn, L, alpha, beta, True)["ck"]
+            return int((ck[:, :K] != blk).any(axis=1).sum())
+        # device generation: codeblock id = offset + b draws from its own Philox counter range
+        m = len(take)
+        crc_len = 24 if crcpoly in ['24A', '24B'] else 16
+        A = K - crc_len
+        poly = {"24A": 3, "24B": 4, "16": 2}[crcpoly]
+        first, stride = offset + take[0], (take[1] - take[0]) if m > 1 else 1
+        fails = 0
+        L_ = _lib.lib()
+        with torch.cuda.device(self.device):
+            for i0 in range(0, m, 8192):
+                mm = min(8192, m - i0)
+                s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                bits = torch.empty((mm, A), dtype=torch.int8, device=self.device)
+                _lib.check(L_.nrldpc_random_bits_rows(bits.data_ptr(), mm, A, seed, first + i0 * stride, stride, s), "random_bits")
+                blk = torch.empty((mm, K), dtype=torch.int8, device=self.device)
+                _lib.check(L_.nrldpc_crc_encode(bits.data_ptr(), mm, A, poly, blk.data_ptr(), s), "crc")
+                dn = engine.encode_batch(blk.clone(), bgn, Zc)
+                llr = torch.empty(dn.shape, dtype=torch.float32, device=self.device)
+                _lib.check(L_.nrldpc_awgn_llr_rows(dn.data_ptr(), mm, dn.shape[1], float(snr_db), seed, first + i0 * stride,
+                                                   stride, llr.data_ptr(), s), "awgn")
+                if algo in ('BF', 'BP'):
+                    h = llr.cpu().numpy().astype(np.float64)
+                    if algo == 'BF':
+                        ck, _, _ = engine.decode_bf_batch(h, Zc, bgn, L)
+                    else:
+                        ck, _, _ = engine.decode_ref_batch(h, Zc, bgn, L, 'BP', 1, 0, True, f64=True)
+                    fails += int((ck[:, :K] != blk.cpu().numpy()).any(axis=1).sum())
+                else:
+                    r = engine.decode_batch(llr, Zc, bgn, L, alpha, beta, True)
+                    cnt = engine.count_errors(blk, r["ck"], K, r["iters"])
+                    fails += int(cnt[1].item())
+        return fails
+
+
+def run_ldpc_simulation(Zc, bgn, crcpoly, algo_list, alpha_list, beta_list, mixed_list, L_list, snr_db_list, filename,
+                        *, rng="numpy", seed=0x5601, backend=None, verbose=True):
+    """Same call and pickle output as scripts/internal/sim_ldpc_internal.run_ldpc_simulation (:9-91)."""
+    d = _Dist()
+    be = backend if backend is not None else CudaBackend()
+    test_results_list, test_config_list = [], []
+    point = 0
+    for flag, algo, L, alpha, beta in test_plan(algo_list, alpha_list, beta_list, mixed_list, L_list):
+        test_config_list.append(flag)
+        bler_result = []
+        for snr_db in snr_db_list:
+            start = time.time()
+            test_count = failed_count = 0
+            while True:
+                nxt = next(c for c in CHECKPOINTS if c > test_count)
+                n = nxt - test_count
+                take = list(range(d.rank, n, d.world))  # this rank's share of the stretch
+                f = be.count_failures(Zc, bgn, snr_db, crcpoly, 'min-sum' if algo in ('NMS', 'OMS', 'mixed-MS') else algo,
+                                      L, alpha, beta, n, take, rng, seed, point * CHECKPOINTS[-1] + test_count)
+                f, = d.sum([f], getattr(be, "reduce_device", None))
+                failed_count += f
+                test_count = nxt
+                if stop_now(test_count, failed_count):
+                    break
+            point += 1
+            bler = failed_count / test_count
+            bler_result.append(bler)
+            if verbose and d.rank == 0:
+                print("finish test {}, Zc {}, bgn{},snr_db={}, test_count={},failed_count={},bler={:2.5f},elpased time: {:6.2f}".
+                      format(flag, Zc, bgn, snr_db, test_count, failed_count, bler, time.time() - start))
+        test_results_list.append(bler_result)
+    sim_config = {'Zc': Zc, 'bgn': bgn}
+    if d.rank == 0 and filename:
+        with open(filename, 'wb') as handle:
+            pickle.dump([sim_config, test_config_list, test_results_list], handle, protocol=pickle.HIGHEST_PROTOCOL)
+    return sim_config, test_config_list, test_results_list
