@@ -37,31 +37,40 @@ namespace nrldpc {
 
 namespace {
 
+constexpr int kMaxS = 16;   // warp groups per warp column
+constexpr int kNumCls = 11; // check-row classes: <19,noext,wide> <10,noext> <8,noext> <10..3,ext>
+
 struct RowInfo {
-    uint32_t mag_off;   // byte offset of the row-block's float2 magnitudes inside a codeblock slot
-    uint32_t bits_off;  // byte offset of its sign/index words
-    uint32_t ext_llr;   // float index of the extension column's LLRs inside a codeblock's LLR row
-    uint16_t e0;        // first edge in cn_edge
-    uint8_t deg, wide;
+    uint32_t mrel;     // i * Zc * 8: byte offset of the row-block's float2 magnitudes inside the mags region;
+                       // its sign words sit at (mrel + r*8)/2 (32-bit) or /4 (16-bit) inside their regions
+    uint32_t ext_llr;  // byte offset of the extension column's LLRs inside a codeblock's LLR row
+    uint32_t e0;       // first edge in the edge table
+    uint32_t pad;
 };
 struct ColInfo {
     uint32_t lq_off;   // byte offset of the column-block's posteriors inside a slot
-    uint32_t llr_off;  // float index of its channel LLRs, or kNoLlr for the punctured columns
-    uint16_t q0;       // first entry in vn_entry
+    uint32_t llr_off;  // byte offset of its channel LLRs inside a codeblock's LLR row, or kNoLlr (punctured)
+    uint16_t q0;       // first entry in the variable-pass table
     uint8_t nwide, deg;
 };
 constexpr uint32_t kNoLlr = 0xffffffffu;
 
-// Everything the kernel needs, by value (constant bank).
+// Everything the kernel needs, by value (constant bank).  The two per-edge tables are staged into
+// shared memory at kernel start (one LDS.64 / LDS.128 per edge instead of constant-bank reads).
 struct DecTab {
     int Zc, Z4, Z8, nrows, ncore, kb, K, N, Nfull, tiles, lanes, lanes_log2, per;
     int G, ncolumns, S, nwarps;
-    int slot_bytes, off_mags, off_bits, off_ext;
-    uint2 cn_edge[kMaxEdges];      // {byte offset of the column's LQ array, shift * 4}
+    int slot_bytes, off_mags, off_bw, off_bn, off_ext;  // off_bn already rebased by -(#wide rows)*Zc*2
+    int tab_cn, tab_vn, smem_bytes;                     // byte offsets of the staged tables, total dynamic smem
+    int nedges, nventries;
+    uint2 cn_edge[kMaxEdges];       // {byte offset of the column's LQ array, shift * 4}
+    uint4 vn_entry[kMaxCoreEdges];  // {row mrel, ((Zc - shift) % Zc) * 8, k << idxshift | (31 - bitpos), 0}
     RowInfo row[kMaxRows];
-    uint4 vn_entry[kMaxCoreEdges]; // {row mag_off, row bits_off, ((Zc - shift) % Zc) * 8, k << idxshift | (31 - bitpos)}
     ColInfo col[kMaxCore];
-    uint8_t cn_order[kMaxRows], vn_order[kMaxCore];
+    uint16_t cls_begin[kNumCls * kMaxS], cls_end[kNumCls * kMaxS];  // ranges of cn_list per (class, warp group)
+    uint8_t cn_list[kMaxRows];
+    uint16_t vn_begin[kMaxS], vn_end[kMaxS];                        // ranges of vn_list per warp group
+    uint8_t vn_list[kMaxCore];
 };
 
 struct DecArgs {
@@ -93,12 +102,21 @@ __device__ __forceinline__ float record_lr(float2 m, bool isidx, uint32_t signwo
     return __uint_as_float(__float_as_uint(mag) ^ (signword & 0x80000000u));
 }
 
-struct Me {            // what a thread owns for the whole kernel
-    char *slot;        // its codeblock's shared-memory slot
-    const float *llr;  // its codeblock's LLR row, already offset by r
-    int g, r;          // slot index, lifted index (clamped to a valid value when !valid)
+struct Me {               // what a thread owns for the whole kernel
+    char *slot;           // its codeblock's shared-memory slot
+    char *mags, *bw, *bn; // slot + off_mags / off_bw / off_bn
+    const char *llr;      // CTA-uniform base of the CTA's first codeblock's LLR row
+    uint32_t llr_off;     // this thread's byte offset from it: (g*N + r) * 4
+    const uint2 *tcn;     // staged edge tables
+    const uint4 *tvn;
+    int g, r;             // slot index, lifted index (clamped to a valid value when !valid)
     bool valid;
 };
+
+__device__ __forceinline__ float load_llr(const Me &me, uint32_t off)
+{
+    return __fadd_rn(__ldg(reinterpret_cast<const float *>(me.llr + (me.llr_off + off))), 0.0f);  // -0.0 -> +0.0
+}
 
 // One check row (row-block i, lifted index r): syndrome bit of the current hard decisions, then the
 // min-sum update of its record from Lq = LQ - Lr_old.  py5gphy/ldpc/nr_ldpc_decode.py:107-123,178-227.
@@ -108,14 +126,16 @@ __device__ __forceinline__ void cn_row(const DecTab &T, const DecArgs &a, const 
 {
     constexpr int SH = WIDE ? 24 : 12;
     constexpr uint32_t IDXMASK = WIDE ? 0x1f000000u : 0xf000u;
+    const RowInfo ri = T.row[i];
     const uint32_t r4 = (uint32_t)me.r * 4u;
-    const uint32_t e0 = T.row[i].e0;
-    char *rec = me.slot + T.row[i].mag_off + 2 * r4;
-    char *bp = me.slot + T.row[i].bits_off + (WIDE ? r4 : r4 >> 1);
+    const uint32_t rel = ri.mrel + 2 * r4;
+    char *rec = me.mags + rel;
+    char *bp = WIDE ? me.bw + (rel >> 1) : me.bn + (rel >> 2);
     const float2 m = *reinterpret_cast<const float2 *>(rec);
     const uint32_t bits = WIDE ? *reinterpret_cast<const uint32_t *>(bp) : *reinterpret_cast<const uint16_t *>(bp);
     float llr_e = 0.f;
-    if (EXT) llr_e = __fadd_rn(__ldg(me.llr + T.row[i].ext_llr), 0.0f);
+    if (EXT) llr_e = load_llr(me, ri.ext_llr);
+    const uint2 *et = me.tcn + ri.e0;
 
     float vmin = __uint_as_float(kInfBits);  // sign = running sign product, |vmin| = first minimum
     float min2 = vmin;
@@ -133,7 +153,7 @@ __device__ __forceinline__ void cn_row(const DecTab &T, const DecArgs &a, const 
                     reinterpret_cast<uint32_t *>(me.slot + T.off_ext)[(i - 4) * T.tiles + (me.r >> 5)] = hb;
             }
         } else {
-            const uint2 ew = T.cn_edge[e0 + k];
+            const uint2 ew = et[k];
             const uint32_t t = r4 + ew.y;
             x = *reinterpret_cast<const float *>(me.slot + ew.x + min(t, t - (uint32_t)T.Z4));
         }
@@ -158,28 +178,28 @@ __device__ __forceinline__ void cn_row(const DecTab &T, const DecArgs &a, const 
     }
 }
 
-template <bool ET>
-__device__ __forceinline__ void cn_dispatch(const DecTab &T, const DecArgs &a, const Me &me, int i, bool active, int *flag)
+// All rows of one class that belong to this warp's group.
+template <int CLS, int DEG, bool EXT, bool WIDE, bool ET>
+__device__ __forceinline__ void cn_class(const DecTab &T, const DecArgs &a, const Me &me, int sub, bool active, int *flag)
 {
-    const int deg = T.row[i].deg;
-    if (i < 4) {
-        switch (deg) {
-        case 19: cn_row<19, false, true, ET>(T, a, me, i, active, flag); break;
-        case 10: cn_row<10, false, false, ET>(T, a, me, i, active, flag); break;
-        default: cn_row<8, false, false, ET>(T, a, me, i, active, flag); break;
-        }
-    } else {
-        switch (deg) {
-        case 3: cn_row<3, true, false, ET>(T, a, me, i, active, flag); break;
-        case 4: cn_row<4, true, false, ET>(T, a, me, i, active, flag); break;
-        case 5: cn_row<5, true, false, ET>(T, a, me, i, active, flag); break;
-        case 6: cn_row<6, true, false, ET>(T, a, me, i, active, flag); break;
-        case 7: cn_row<7, true, false, ET>(T, a, me, i, active, flag); break;
-        case 8: cn_row<8, true, false, ET>(T, a, me, i, active, flag); break;
-        case 9: cn_row<9, true, false, ET>(T, a, me, i, active, flag); break;
-        default: cn_row<10, true, false, ET>(T, a, me, i, active, flag); break;
-        }
-    }
+    const int e = T.cls_end[CLS * kMaxS + sub];
+    for (int o = T.cls_begin[CLS * kMaxS + sub]; o < e; ++o) cn_row<DEG, EXT, WIDE, ET>(T, a, me, T.cn_list[o], active, flag);
+}
+
+template <bool ET>
+__device__ __forceinline__ void cn_pass(const DecTab &T, const DecArgs &a, const Me &me, int sub, bool active, int *flag)
+{
+    cn_class<0, 19, false, true, ET>(T, a, me, sub, active, flag);
+    cn_class<1, 10, false, false, ET>(T, a, me, sub, active, flag);
+    cn_class<2, 8, false, false, ET>(T, a, me, sub, active, flag);
+    cn_class<3, 10, true, false, ET>(T, a, me, sub, active, flag);
+    cn_class<4, 9, true, false, ET>(T, a, me, sub, active, flag);
+    cn_class<5, 8, true, false, ET>(T, a, me, sub, active, flag);
+    cn_class<6, 7, true, false, ET>(T, a, me, sub, active, flag);
+    cn_class<7, 6, true, false, ET>(T, a, me, sub, active, flag);
+    cn_class<8, 5, true, false, ET>(T, a, me, sub, active, flag);
+    cn_class<9, 4, true, false, ET>(T, a, me, sub, active, flag);
+    cn_class<10, 3, true, false, ET>(T, a, me, sub, active, flag);
 }
 
 // One core variable (column-block j, lifted index c = me.r): LQ = LLRin + sum_i Lr(i) in ascending
@@ -188,51 +208,52 @@ __device__ __forceinline__ void vn_col(const DecTab &T, const Me &me, int j, boo
 {
     const ColInfo ci = T.col[j];
     float lv = 0.f;  // the 2Zc punctured systematic bits start at LLR 0 (:43)
-    if (ci.llr_off != kNoLlr) lv = __fadd_rn(__ldg(me.llr + ci.llr_off), 0.0f);
+    if (ci.llr_off != kNoLlr) lv = load_llr(me, ci.llr_off);
     const uint32_t c8 = (uint32_t)me.r * 8u, Z8 = (uint32_t)T.Z8;
     float acc = 0.f;
-    int q = ci.q0;
-    const int qw = q + ci.nwide, qe = q + ci.deg;
+    const uint4 *q = me.tvn + ci.q0;
+    const uint4 *qw = q + ci.nwide, *qe = q + ci.deg;
     for (; q < qw; ++q) {  // rows with 32-bit sign words (BG1 rows 0-3) come first: ascending row order
-        const uint4 en = T.vn_entry[q];
-        const uint32_t t = c8 + en.z, r8 = min(t, t - Z8);
-        const float2 m = *reinterpret_cast<const float2 *>(me.slot + en.x + r8);
-        const uint32_t bits = *reinterpret_cast<const uint32_t *>(me.slot + en.y + (r8 >> 1));
-        acc = __fadd_rn(acc, record_lr(m, ((bits ^ en.w) & 0x1f000000u) == 0, bits << (en.w & 31u)));
+        const uint4 en = *q;
+        const uint32_t t = c8 + en.y, rel = en.x + min(t, t - Z8);
+        const float2 m = *reinterpret_cast<const float2 *>(me.mags + rel);
+        const uint32_t bits = *reinterpret_cast<const uint32_t *>(me.bw + (rel >> 1));
+        acc = __fadd_rn(acc, record_lr(m, ((bits ^ en.z) & 0x1f000000u) == 0, bits << (en.z & 31u)));
     }
 #pragma unroll 4
     for (; q < qe; ++q) {
-        const uint4 en = T.vn_entry[q];
-        const uint32_t t = c8 + en.z, r8 = min(t, t - Z8);
-        const float2 m = *reinterpret_cast<const float2 *>(me.slot + en.x + r8);
-        const uint32_t bits = *reinterpret_cast<const uint16_t *>(me.slot + en.y + (r8 >> 2));
-        acc = __fadd_rn(acc, record_lr(m, ((bits ^ en.w) & 0xf000u) == 0, bits << (en.w & 31u)));
+        const uint4 en = *q;
+        const uint32_t t = c8 + en.y, rel = en.x + min(t, t - Z8);
+        const float2 m = *reinterpret_cast<const float2 *>(me.mags + rel);
+        const uint32_t bits = *reinterpret_cast<const uint16_t *>(me.bn + (rel >> 2));
+        acc = __fadd_rn(acc, record_lr(m, ((bits ^ en.z) & 0xf000u) == 0, bits << (en.z & 31u)));
     }
     if (active) *reinterpret_cast<float *>(me.slot + ci.lq_off + (c8 >> 1)) = __fadd_rn(lv, acc);
 }
 
-// Syndrome pass without a record update.  FINAL: the post-loop tie rule LQ<=0 -> 1
-// (py5gphy/ldpc/nr_ldpc_decode.py:134-143); otherwise LQ<0 -> 1 (:107-111).  Also stores the hard
-// decisions of the extension variables, which have no resident posterior.
-template <bool FINAL>
-__device__ __forceinline__ void syndrome_row(const DecTab &T, const Me &me, int i, bool active, int *flag)
+// Syndrome pass without a record update, with the post-loop tie rule LQ<=0 -> 1
+// (py5gphy/ldpc/nr_ldpc_decode.py:134-143).  Also stores the hard decisions of the extension
+// variables, which have no resident posterior.
+__device__ __forceinline__ void final_row(const DecTab &T, const Me &me, int i, bool active, int *flag)
 {
     const RowInfo ri = T.row[i];
     const uint32_t r4 = (uint32_t)me.r * 4u;
-    const int ncoredeg = (i >= 4) ? ri.deg - 1 : ri.deg;
+    const int deg = (i + 1 < T.nrows ? T.row[i + 1].e0 : T.nedges) - ri.e0;
+    const int ncoredeg = (i >= 4) ? deg - 1 : deg;
     uint32_t synd = 0;
     for (int k = 0; k < ncoredeg; ++k) {
-        const uint2 ew = T.cn_edge[ri.e0 + k];
+        const uint2 ew = me.tcn[ri.e0 + k];
         const uint32_t t = r4 + ew.y;
         const float x = *reinterpret_cast<const float *>(me.slot + ew.x + min(t, t - (uint32_t)T.Z4));
-        synd ^= (FINAL ? (x <= 0.f) : (x < 0.f)) ? 1u : 0u;
+        synd ^= (x <= 0.f) ? 1u : 0u;
     }
     if (i >= 4) {
-        const float2 m = *reinterpret_cast<const float2 *>(me.slot + ri.mag_off + 2 * r4);
-        const uint32_t bits = *reinterpret_cast<const uint16_t *>(me.slot + ri.bits_off + (r4 >> 1));
-        const float lr = record_lr(m, ((bits ^ ((uint32_t)(ri.deg - 1) << 12)) & 0xf000u) == 0, bits << 31);
-        const float x = __fadd_rn(__fadd_rn(__ldg(me.llr + ri.ext_llr), 0.0f), lr);
-        const bool hb1 = FINAL ? (x <= 0.f) : (x < 0.f);
+        const uint32_t rel = ri.mrel + 2 * r4;
+        const float2 m = *reinterpret_cast<const float2 *>(me.mags + rel);
+        const uint32_t bits = *reinterpret_cast<const uint16_t *>(me.bn + (rel >> 2));
+        const float lr = record_lr(m, ((bits ^ ((uint32_t)(deg - 1) << 12)) & 0xf000u) == 0, bits << 31);
+        const float x = __fadd_rn(load_llr(me, ri.ext_llr), lr);
+        const bool hb1 = x <= 0.f;
         const uint32_t hb = __ballot_sync(0xffffffffu, hb1);
         if (active && (me.r & (T.lanes - 1)) == 0)
             reinterpret_cast<uint32_t *>(me.slot + T.off_ext)[(i - 4) * T.tiles + (me.r >> 5)] = hb;
@@ -248,7 +269,7 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
     extern __shared__ __align__(16) char smem[];
     __shared__ int s_flag[2][kMaxG];
     const int Zc = T.Zc, tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
-    const int warp = __reduce_min_sync(0xffffffffu, tid >> 5);  // REDUX result lives in a uniform register
+    const int warp = __reduce_min_sync(0xffffffffu, tid >> 5);  // warp-uniform (REDUX writes a uniform register)
     const int G = T.G, cb0 = blockIdx.x * G;
 
     // ---- the (codeblock, r) this thread owns, and the row-/column-block subset of its warp
@@ -262,14 +283,24 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
         me.g = g;
         me.r = (r < Zc) ? r : 0;
         me.slot = smem + g * T.slot_bytes;
-        me.llr = a.llr + (size_t)((cb < a.B) ? cb : a.B - 1) * T.N + me.r;
+        me.mags = me.slot + T.off_mags;
+        me.bw = me.slot + T.off_bw;
+        me.bn = me.slot + T.off_bn;
+        me.llr = reinterpret_cast<const char *>(a.llr + (size_t)cb0 * T.N);
+        me.llr_off = (uint32_t)(((cb < a.B) ? g : a.B - 1 - cb0) * T.N + me.r) * 4u;
+        me.tcn = reinterpret_cast<const uint2 *>(smem + T.tab_cn);
+        me.tvn = reinterpret_cast<const uint4 *>(smem + T.tab_vn);
     }
 
-    // ---- init: records = 0 (Lr = 0, :101), LQ = LLRin (:94) with the punctured columns at 0 (:43)
+    // ---- init: records = 0 (Lr = 0, :101), tables staged, LQ = LLRin (:94) with the punctured columns at 0 (:43)
     {
         uint32_t *w = reinterpret_cast<uint32_t *>(smem);
         const int nw = G * T.slot_bytes / 4;
         for (int t = tid; t < nw; t += NT) w[t] = 0;
+        uint2 *tc = reinterpret_cast<uint2 *>(smem + T.tab_cn);
+        for (int t = tid; t < T.nedges; t += NT) tc[t] = T.cn_edge[t];
+        uint4 *tv = reinterpret_cast<uint4 *>(smem + T.tab_vn);
+        for (int t = tid; t < T.nventries; t += NT) tv[t] = T.vn_entry[t];
         if (tid < kMaxG) { s_flag[0][tid] = 0; s_flag[1][tid] = 0; }
     }
     __syncthreads();
@@ -280,8 +311,7 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
     if (me.valid)
         for (int o = sub; o < T.ncore; o += T.S) {
             const ColInfo ci = T.col[o];
-            if (ci.llr_off != kNoLlr)
-                *reinterpret_cast<float *>(me.slot + ci.lq_off + me.r * 4) = __fadd_rn(__ldg(me.llr + ci.llr_off), 0.0f);
+            if (ci.llr_off != kNoLlr) *reinterpret_cast<float *>(me.slot + ci.lq_off + me.r * 4) = load_llr(me, ci.llr_off);
         }
     __syncthreads();
 
@@ -292,8 +322,7 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
         int *flag = s_flag[it & 1];
         const bool active = me.valid && !((donemask >> me.g) & 1u);
         // ---- check-node pass (+ syndrome of the current hard decisions when ET)
-        if (__any_sync(0xffffffffu, active))
-            for (int o = sub; o < T.nrows; o += T.S) cn_dispatch<ET>(T, a, me, T.cn_order[o], active, flag);
+        if (__any_sync(0xffffffffu, active)) cn_pass<ET>(T, a, me, sub, active, flag);
         __syncthreads();
         if (ET) {
             for (int g = 0; g < G; ++g)
@@ -307,8 +336,10 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
         }
         // ---- variable-node pass
         const bool active2 = me.valid && !((donemask >> me.g) & 1u);
-        if (__any_sync(0xffffffffu, active2))
-            for (int o = sub; o < T.ncore; o += T.S) vn_col(T, me, T.vn_order[o], active2);
+        if (__any_sync(0xffffffffu, active2)) {
+            const int e = T.vn_end[sub];
+            for (int o = T.vn_begin[sub]; o < e; ++o) vn_col(T, me, T.vn_list[o], active2);
+        }
         __syncthreads();
     }
 
@@ -317,7 +348,7 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
     if (donemask != fullmask) {
         int *flag = s_flag[it & 1];  // cleared, not yet written
         const bool active = me.valid && !((donemask >> me.g) & 1u);
-        for (int o = sub; o < T.nrows; o += T.S) syndrome_row<true>(T, me, o, active, flag);
+        for (int o = sub; o < T.nrows; o += T.S) final_row(T, me, o, active, flag);
         __syncthreads();
         for (int g = 0; g < G; ++g)
             if (!((donemask >> g) & 1u) && flag[g] == 0) okmask |= 1u << g;
@@ -367,6 +398,12 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
 
 constexpr int kSmemMax = 227 * 1024 - 512;  // 227 KB per CTA minus the static flags
 
+int class_of(int i, int deg)
+{
+    if (i < 4) return deg == 19 ? 0 : (deg == 10 ? 1 : (deg == 8 ? 2 : -1));
+    return (deg >= 3 && deg <= 10) ? 13 - deg : -1;  // 10 -> 3 ... 3 -> 10
+}
+
 // Host: derive the kernel tables and launch geometry for one (bgn, Zc).
 int build_dec_tab(const QcCfg &c, DecTab *T)
 {
@@ -375,13 +412,22 @@ int build_dec_tab(const QcCfg &c, DecTab *T)
     T->Zc = Zc; T->Z4 = 4 * Zc; T->Z8 = 8 * Zc;
     T->nrows = c.nrows; T->ncore = c.ncore; T->kb = c.kb; T->K = c.K; T->N = c.N; T->Nfull = c.Nfull;
     T->tiles = c.tiles; T->lanes = c.lanes; T->lanes_log2 = c.lanes_log2; T->per = c.per;
+    T->nedges = c.rowptr[c.nrows]; T->nventries = c.colptr[c.ncore];
+    // rows with 32-bit sign words must be the leading row-blocks (BG1: 0-3, BG2: none)
+    int nwide_rows = 0;
+    for (int i = 0; i < c.nrows; ++i) {
+        if (c.wide[i]) { if (i != nwide_rows) return NRLDPC_EINVAL; ++nwide_rows; }
+    }
     // slot layout
     T->off_mags = (c.ncore * Zc * 4 + 7) & ~7;
-    T->off_bits = T->off_mags + c.nrows * Zc * 8;
-    T->off_ext = (T->off_bits + c.bits_bytes_per_zc * Zc + 3) & ~3;
+    T->off_bw = T->off_mags + c.nrows * Zc * 8;
+    const int bn_start = T->off_bw + nwide_rows * Zc * 4;
+    T->off_bn = bn_start - nwide_rows * Zc * 2;  // so that row i >= nwide_rows lands at off_bn + (i*Zc + r)*2
+    T->off_ext = (bn_start + (c.nrows - nwide_rows) * Zc * 2 + 3) & ~3;
     T->slot_bytes = (T->off_ext + (c.nrows - 4) * c.tiles * 4 + 15) & ~15;
+    const int tab_bytes = T->nedges * 8 + T->nventries * 16;
     // geometry: as many codeblocks per CTA as fit, at most 16 warp columns and 32 codeblocks
-    int gmax = kSmemMax / T->slot_bytes;
+    int gmax = (kSmemMax - tab_bytes) / T->slot_bytes;
     if (gmax < 1) return NRLDPC_EINVAL;
     gmax = std::min(gmax, kMaxG);
     int G = std::min(gmax, std::max(1, 16 / c.tiles) * c.per);
@@ -389,29 +435,31 @@ int build_dec_tab(const QcCfg &c, DecTab *T)
     if (G > gmax) return NRLDPC_EINVAL;
     T->G = G;
     T->ncolumns = (G / c.per) * c.tiles;
-    T->S = std::max(1, 32 / T->ncolumns);
+    T->S = std::min(kMaxS, std::max(1, 32 / T->ncolumns));
     T->nwarps = T->ncolumns * T->S;
     if (T->nwarps > 32) return NRLDPC_EINVAL;
+    T->tab_vn = G * T->slot_bytes;  // 16-byte aligned
+    T->tab_cn = T->tab_vn + T->nventries * 16;
+    T->smem_bytes = T->tab_cn + T->nedges * 8;
+    const int S = T->S;
 
+    std::vector<int> deg(c.nrows);
     for (int i = 0; i < c.nrows; ++i) {
         RowInfo &r = T->row[i];
-        r.mag_off = T->off_mags + i * Zc * 8;
-        r.bits_off = T->off_bits + c.bits_off[i] * Zc;
-        r.ext_llr = (i >= 4) ? (uint32_t)(c.kb + i - 2) * Zc : 0;
+        r.mrel = (uint32_t)i * Zc * 8;
+        r.ext_llr = (i >= 4) ? (uint32_t)(c.kb + i - 2) * Zc * 4 : 0;
         r.e0 = c.rowptr[i];
-        r.deg = (uint8_t)(c.rowptr[i + 1] - c.rowptr[i]);
-        r.wide = c.wide[i];
-        const bool okdeg = (i < 4) ? (r.deg == 19 || r.deg == 10 || r.deg == 8) : (r.deg >= 3 && r.deg <= 10);
-        if (!okdeg || (r.wide != (r.deg == 19))) return NRLDPC_EINVAL;
+        deg[i] = c.rowptr[i + 1] - c.rowptr[i];
+        if (class_of(i, deg[i]) < 0 || (c.wide[i] != 0) != (deg[i] == 19)) return NRLDPC_EINVAL;
     }
-    for (int e = 0; e < c.rowptr[c.nrows]; ++e) {
+    for (int e = 0; e < T->nedges; ++e) {
         const int j = c.edge[e] & 0xff, P = c.edge[e] >> 8;
         T->cn_edge[e] = make_uint2((uint32_t)(j < c.ncore ? j * Zc * 4 : 0), (uint32_t)P * 4);
     }
     for (int j = 0; j < c.ncore; ++j) {
         ColInfo &ci = T->col[j];
         ci.lq_off = j * Zc * 4;
-        ci.llr_off = j >= 2 ? (uint32_t)(j - 2) * Zc : kNoLlr;
+        ci.llr_off = j >= 2 ? (uint32_t)(j - 2) * Zc * 4 : kNoLlr;
         ci.q0 = c.colptr[j];
         ci.deg = (uint8_t)(c.colptr[j + 1] - c.colptr[j]);
         int nwide = 0;
@@ -419,37 +467,49 @@ int build_dec_tab(const QcCfg &c, DecTab *T)
             const uint32_t en = c.centry[q];
             const int i = en & 63, k = (en >> 6) & 31, bitpos = (en >> 11) & 31, back = en >> 16;
             const bool wide = c.wide[i];
-            if (wide) { if (nwide != q - c.colptr[j]) return NRLDPC_EINVAL; ++nwide; }  // wide rows must lead
-            T->vn_entry[q] = make_uint4(T->row[i].mag_off, T->row[i].bits_off, (uint32_t)back * 8,
-                                        ((uint32_t)k << (wide ? 24 : 12)) | (uint32_t)(31 - bitpos));
+            if (wide) { if (nwide != q - c.colptr[j]) return NRLDPC_EINVAL; ++nwide; }  // wide rows lead (ascending i)
+            T->vn_entry[q] = make_uint4(T->row[i].mrel, (uint32_t)back * 8,
+                                        ((uint32_t)k << (wide ? 24 : 12)) | (uint32_t)(31 - bitpos), 0u);
         }
         ci.nwide = (uint8_t)nwide;
     }
-    // balanced static split: rank by degree, deal to the S warp groups in snake order
-    auto deal = [&](int n, auto degree, uint8_t *order) {
-        std::vector<int> idx(n);
-        for (int i = 0; i < n; ++i) idx[i] = i;
-        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return degree(x) > degree(y); });
-        const int S = T->S;
+    // check rows: per class, deal the rows round-robin to the S warp groups, continuing the rotation
+    // across classes so that no group collects all the remainders
+    {
+        std::vector<std::vector<std::vector<int>>> lists(kNumCls, std::vector<std::vector<int>>(S));
+        int rot = 0;
+        for (int cls = 0; cls < kNumCls; ++cls)
+            for (int i = 0; i < c.nrows; ++i)
+                if (class_of(i, deg[i]) == cls) lists[cls][rot++ % S].push_back(i);
+        int pos = 0;
+        for (int cls = 0; cls < kNumCls; ++cls)
+            for (int s = 0; s < S; ++s) {
+                T->cls_begin[cls * kMaxS + s] = (uint16_t)pos;
+                for (int i : lists[cls][s]) T->cn_list[pos++] = (uint8_t)i;
+                T->cls_end[cls * kMaxS + s] = (uint16_t)pos;
+            }
+        if (pos != c.nrows) return NRLDPC_EINVAL;
+    }
+    // core columns: longest-processing-time-first onto the S groups
+    {
+        std::vector<int> idx(c.ncore);
+        for (int j = 0; j < c.ncore; ++j) idx[j] = j;
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return T->col[x].deg > T->col[y].deg; });
         std::vector<std::vector<int>> grp(S);
-        for (int p = 0; p < n; ++p) {
-            const int round = p / S, pos = p % S;
-            const bool partial = (round + 1) * S > n;  // the last, incomplete round fills groups 0..rem-1
-            grp[((round & 1) && !partial) ? S - 1 - pos : pos].push_back(idx[p]);
+        std::vector<int> load(S, 0);
+        for (int j : idx) {
+            int best = 0;
+            for (int s = 1; s < S; ++s) if (load[s] < load[best]) best = s;
+            grp[best].push_back(j);
+            load[best] += T->col[j].deg + 3;
         }
-        // order[o] for o = s, s+S, ... must enumerate group s
-        std::vector<int> out(n, -1);
-        for (int s = 0; s < S; ++s)
-            for (size_t t = 0; t < grp[s].size(); ++t)
-                if ((int)(s + t * S) < n) out[s + t * S] = grp[s][t];
-        for (int o = 0; o < n; ++o) {
-            if (out[o] < 0) return false;
-            order[o] = (uint8_t)out[o];
+        int pos = 0;
+        for (int s = 0; s < S; ++s) {
+            T->vn_begin[s] = (uint16_t)pos;
+            for (int j : grp[s]) T->vn_list[pos++] = (uint8_t)j;
+            T->vn_end[s] = (uint16_t)pos;
         }
-        return true;
-    };
-    if (!deal(c.nrows, [&](int i) { return (int)T->row[i].deg; }, T->cn_order)) return NRLDPC_EINVAL;
-    if (!deal(c.ncore, [&](int j) { return (int)T->col[j].deg; }, T->vn_order)) return NRLDPC_EINVAL;
+    }
     return NRLDPC_OK;
 }
 
@@ -475,7 +535,7 @@ int decode_minsum_geometry(const QcCfg &cfg, int *G_out, int *threads, int *smem
     if (!T) return NRLDPC_EINVAL;
     if (G_out) *G_out = T->G;
     if (threads) *threads = T->nwarps * 32;
-    if (smem) *smem = T->G * T->slot_bytes;
+    if (smem) *smem = T->smem_bytes;
     return NRLDPC_OK;
 }
 
@@ -489,7 +549,7 @@ int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_it
     DecArgs a;
     a.llr = d_llr; a.B = B; a.max_iter = max_iter; a.alpha = alpha; a.beta = beta;
     a.ck = d_ck; a.info = d_info; a.status = d_status; a.iters = d_iters;
-    const int grid = (B + T->G - 1) / T->G, nt = T->nwarps * 32, smem = T->G * T->slot_bytes;
+    const int grid = (B + T->G - 1) / T->G, nt = T->nwarps * 32, smem = T->smem_bytes;
     auto launch = [&](auto kern) -> int {
         NRLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<grid, nt, smem, s>>>(*T, a);
