@@ -34,9 +34,7 @@
 
 #include <utility>
 
-#include "nrldpc_common.cuh"
-#define NRLDPC_TABLE static constexpr
-#include "../../include/nrldpc_bg_tables.inc"
+#include "nrldpc_decode.cuh"
 
 namespace nrldpc {
 
@@ -78,35 +76,7 @@ struct DecTab {
     uint8_t vn_list[kMaxCore];
 };
 
-struct DecArgs {
-    const float *llr;
-    int B, max_iter;
-    float alpha, beta;
-    int8_t *ck;
-    uint32_t *info;
-    uint8_t *status;
-    int32_t *iters;
-};
-
 constexpr int kMaxG = 32;
-constexpr uint32_t kInfBits = 0x7f800000u;
-
-// d = min(|a|,|b|) with sign(a) xor sign(b): running "sign product * first minimum" of a check row.
-__device__ __forceinline__ float min_xorsign_abs(float a, float b)
-{
-    float d;
-    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-    return d;
-}
-
-// Check-to-variable message decoded from a row record: magnitude m.y on the argmin edge (isidx),
-// m.x elsewhere; `signword` carries the edge's sign in bit 31.
-__device__ __forceinline__ float record_lr(float2 m, bool isidx, uint32_t signword)
-{
-    const float mag = isidx ? m.y : m.x;
-    return __uint_as_float(__float_as_uint(mag) ^ (signword & 0x80000000u));
-}
-
 struct Me {               // what a thread owns for the whole kernel
     char *slot;           // its codeblock's shared-memory slot
     char *mags, *bw, *bn; // slot + off_mags / off_bw / off_bn
@@ -533,410 +503,14 @@ const DecTab *get_dec_tab(const QcCfg &cfg)
 }
 
 
-// =====================================================================================================
-// Specialised kernels: (bgn, Zc) known at compile time.
-//
-// The generic kernel above spends ~1/3 of its instructions on table reads, table-driven address
-// arithmetic and loop control.  For the lifting sizes that carry the traffic (the headline BG1 Zc=384)
-// the whole base graph is unrolled at compile time from the constexpr TS 38.212 tables: every shift,
-// column offset, record offset and sign-bit position becomes an immediate, each warp group executes
-// straight-line code for its own row-/column-blocks, and shared-memory accesses use [R + imm].
-// Semantics, data layout and summation order are identical to the generic kernel (same tests).
-namespace spec {
-
-template <int BGN> struct Graph;
-template <> struct Graph<1> {
-    static constexpr int rows = NRLDPC_BG1_ROWS, cols = NRLDPC_BG1_COLS, nnz = NRLDPC_BG1_NNZ, kb = 22;
-    static constexpr int rowptr(int i) { return nrldpc_bg1_rowptr[i]; }
-    static constexpr int col(int e) { return nrldpc_bg1_col[e]; }
-    static constexpr int shift(int s, int e) { return nrldpc_bg1_shift[s][e]; }
-};
-template <> struct Graph<2> {
-    static constexpr int rows = NRLDPC_BG2_ROWS, cols = NRLDPC_BG2_COLS, nnz = NRLDPC_BG2_NNZ, kb = 10;
-    static constexpr int rowptr(int i) { return nrldpc_bg2_rowptr[i]; }
-    static constexpr int col(int e) { return nrldpc_bg2_col[e]; }
-    static constexpr int shift(int s, int e) { return nrldpc_bg2_shift[s][e]; }
-};
-
-constexpr int ils_of(int Zc)
-{
-    constexpr int a[8] = {2, 3, 5, 7, 9, 11, 13, 15};
-    for (int s = 0; s < 8; ++s)
-        for (int z = a[s]; z <= 384; z *= 2)
-            if (z == Zc) return s;
-    return -1;
-}
-
-template <int BGN, int ZC_> struct Code {
-    using G = Graph<BGN>;
-    static constexpr int bgn = BGN, ZC = ZC_, iLS = ils_of(ZC_);
-    static_assert(iLS >= 0 && ZC_ % 32 == 0, "specialised kernels need a lifting size that is a multiple of 32");
-    static constexpr int nrows = G::rows, kb = G::kb, ncore = G::kb + 4, nnz = G::nnz;
-    static constexpr int K = kb * ZC, N = (G::cols - 2) * ZC, Nfull = G::cols * ZC;
-    static constexpr int tiles = ZC / 32, S = (32 / tiles) < kMaxS ? (32 / tiles) : kMaxS, nwarps = tiles * S;
-    static constexpr int deg(int i) { return G::rowptr(i + 1) - G::rowptr(i); }
-    static constexpr int nwide = (deg(0) > 12) ? 4 : 0;
-    // slot layout: identical to build_dec_tab (checked on the host before the first launch)
-    static constexpr int off_mags = (ncore * ZC * 4 + 7) & ~7;
-    static constexpr int off_bw = off_mags + nrows * ZC * 8;
-    static constexpr int bn_start = off_bw + nwide * ZC * 4;
-    static constexpr int off_bn = bn_start - nwide * ZC * 2;
-    static constexpr int off_ext = (bn_start + (nrows - nwide) * ZC * 2 + 3) & ~3;
-    static constexpr int slot_bytes = (off_ext + (nrows - 4) * tiles * 4 + 15) & ~15;
-    static constexpr int P(int e) { return G::shift(iLS, e) % ZC; }
-    static constexpr int row_of(int e) { int i = 0; while (G::rowptr(i + 1) <= e) ++i; return i; }
-    // column view, ascending row-block = the reference's summation order
-    static constexpr int cdeg(int j) { int n = 0; for (int e = 0; e < nnz; ++e) n += (G::col(e) == j); return n; }
-    static constexpr int cedge(int j, int n)
-    {
-        for (int e = 0; e < nnz; ++e)
-            if (G::col(e) == j && n-- == 0) return e;
-        return -1;
-    }
-};
-
-struct Deal { int n[kMaxS]; int item[kMaxS][kMaxRows]; };
-
-// rows by degree (descending, stable), dealt round-robin to the S warp groups
-template <class C> constexpr Deal deal_rows()
-{
-    Deal d{};
-    int order[kMaxRows] = {};
-    for (int i = 0; i < C::nrows; ++i) order[i] = i;
-    for (int i = 1; i < C::nrows; ++i)  // insertion sort, stable
-        for (int p = i; p > 0 && C::deg(order[p - 1]) < C::deg(order[p]); --p) { int t = order[p]; order[p] = order[p - 1]; order[p - 1] = t; }
-    for (int p = 0; p < C::nrows; ++p) { const int s = p % C::S; d.item[s][d.n[s]++] = order[p]; }
-    return d;
-}
-// core columns: longest-processing-time-first onto the S groups
-template <class C> constexpr Deal deal_cols()
-{
-    Deal d{};
-    int order[kMaxRows] = {}, load[kMaxS] = {};
-    for (int j = 0; j < C::ncore; ++j) order[j] = j;
-    for (int i = 1; i < C::ncore; ++i)
-        for (int p = i; p > 0 && C::cdeg(order[p - 1]) < C::cdeg(order[p]); --p) { int t = order[p]; order[p] = order[p - 1]; order[p - 1] = t; }
-    for (int p = 0; p < C::ncore; ++p) {
-        int best = 0;
-        for (int s = 1; s < C::S; ++s) if (load[s] < load[best]) best = s;
-        d.item[best][d.n[best]++] = order[p];
-        load[best] += C::cdeg(order[p]) + 2;
-    }
-    return d;
-}
-template <class C> inline constexpr Deal kRows = deal_rows<C>();
-template <class C> inline constexpr Deal kCols = deal_cols<C>();
-
-struct Th {            // per-thread constants
-    char *smem;        // the CTA's single codeblock slot
-    const float *llr;  // this thread's codeblock LLR row, already offset by r
-    uint32_t r4;       // r * 4
-    int r;
-    bool active;
-};
-
-struct RowState { float vmin, min2; uint32_t nidx, sacc, synd; };
-
-template <class C, int I, int K, bool ET>
-__device__ __forceinline__ void cn_edge_s(RowState &st, const Th &th, float2 m, uint32_t bits, float llr_e)
-{
-    constexpr int DEG = C::deg(I), e = C::G::rowptr(I) + K;
-    constexpr bool EXT = I >= 4, WIDE = DEG > 12;
-    constexpr int SH = WIDE ? 24 : 12;
-    constexpr uint32_t IDXMASK = WIDE ? 0x1f000000u : 0xf000u;
-    const bool isidx = ((bits ^ ((uint32_t)K << SH)) & IDXMASK) == 0;
-    const float lr = record_lr(m, isidx, bits << (31 - (DEG - 1 - K)));
-    float x;
-    if constexpr (EXT && K == DEG - 1) {
-        x = __fadd_rn(llr_e, lr);  // posterior of the degree-1 extension variable (:126)
-        if constexpr (ET) {
-            const uint32_t hb = __ballot_sync(0xffffffffu, x < 0.f);
-            if (th.active && (th.r & 31) == 0)
-                reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + (th.r >> 5)] = hb;
-        }
-    } else {
-        constexpr uint32_t P4 = 4u * C::P(e), Z4 = 4u * C::ZC, lq = 4u * C::ZC * C::G::col(e);
-        uint32_t w = th.r4;
-        if constexpr (P4 != 0) { const uint32_t t = th.r4 + P4; w = min(t, t - Z4); }  // (r + P) mod Zc
-        x = *reinterpret_cast<const float *>(th.smem + lq + w);
-    }
-    if constexpr (ET) st.synd ^= __float_as_uint(x);  // sign bit = hard decision LQ<0 (:107-108)
-    const float q = __fsub_rn(x, lr);                  // Lq = LQ - Lr (:131)
-    const float aq = fabsf(q), a1 = fabsf(st.vmin);
-    st.min2 = fminf(st.min2, fmaxf(a1, aq));
-    st.nidx = (aq < a1) ? (uint32_t)K << SH : st.nidx;
-    st.vmin = min_xorsign_abs(st.vmin, q);
-    st.sacc = __funnelshift_l(__float_as_uint(q), st.sacc, 1);  // sign of Lq on edge K -> bit DEG-1-K
-}
-
-template <class C, int I, bool ET, int... K>
-__device__ __forceinline__ void cn_edges_s(RowState &st, const Th &th, float2 m, uint32_t bits, float llr_e,
-                                           std::integer_sequence<int, K...>)
-{
-    (cn_edge_s<C, I, K, ET>(st, th, m, bits, llr_e), ...);
-}
-
-// One check row of row-block I (compile time), lifted index r: see cn_row above.
-template <class C, int I, bool ET>
-__device__ __forceinline__ void cn_row_s(const DecArgs &a, Th th, int *flag)
-{
-    // r4 is made opaque per row: otherwise every (r + P) mod Zc of the whole graph is loop-invariant,
-    // gets hoisted out of the iteration loop and spills (hundreds of live values per thread)
-    asm volatile("" : "+r"(th.r4));
-    constexpr int DEG = C::deg(I);
-    constexpr bool EXT = I >= 4, WIDE = DEG > 12;
-    char *rec = th.smem + (C::off_mags + I * C::ZC * 8) + 2 * th.r4;
-    char *bp = WIDE ? th.smem + (C::off_bw + I * C::ZC * 4) + th.r4 : th.smem + (C::off_bn + I * C::ZC * 2) + (th.r4 >> 1);
-    const float2 m = *reinterpret_cast<const float2 *>(rec);
-    const uint32_t bits = WIDE ? *reinterpret_cast<const uint32_t *>(bp) : *reinterpret_cast<const uint16_t *>(bp);
-    float llr_e = 0.f;
-    if constexpr (EXT) llr_e = __fadd_rn(__ldg(th.llr + (C::kb + I - 2) * C::ZC), 0.0f);
-    RowState st{__uint_as_float(kInfBits), __uint_as_float(kInfBits), 0u, 0u, 0u};
-    cn_edges_s<C, I, ET>(st, th, m, bits, llr_e, std::make_integer_sequence<int, DEG>{});
-    const float mag1 = __fmul_rn(a.alpha, fmaxf(__fsub_rn(fabsf(st.vmin), a.beta), 0.f));
-    const float mag2 = __fmul_rn(a.alpha, fmaxf(__fsub_rn(st.min2, a.beta), 0.f));
-    const uint32_t sp = (uint32_t)((int)__float_as_uint(st.vmin) >> 31);
-    const uint32_t nb = ((st.sacc ^ sp) & ((1u << DEG) - 1u)) | st.nidx;
-    if (th.active) {
-        *reinterpret_cast<float2 *>(rec) = make_float2(mag1, mag2);
-        if constexpr (WIDE) *reinterpret_cast<uint32_t *>(bp) = nb;
-        else *reinterpret_cast<uint16_t *>(bp) = (uint16_t)nb;
-        if (ET && (st.synd >> 31)) flag[0] = 1;
-    }
-}
-
-template <class C, bool ET, int SUB, int O = 0>
-__device__ __forceinline__ void cn_pass_s(const DecArgs &a, const Th &th, int *flag)
-{
-    if constexpr (O < kRows<C>.n[SUB]) {
-        cn_row_s<C, kRows<C>.item[SUB][O], ET>(a, th, flag);
-        asm volatile("" ::: "memory");  // keep the rows' loads from being hoisted across each other (register pressure)
-        cn_pass_s<C, ET, SUB, O + 1>(a, th, flag);
-    }
-}
-
-template <class C, int J, int Nn>
-__device__ __forceinline__ void vn_entry_s(float &acc, const Th &th, uint32_t c2)
-{
-    constexpr int e = C::cedge(J, Nn), i = C::row_of(e), k = e - C::G::rowptr(i), DEGI = C::deg(i);
-    constexpr bool WIDE = DEGI > 12;
-    constexpr uint32_t back2 = 2u * ((C::ZC - C::P(e)) % C::ZC), Z2 = 2u * C::ZC;
-    uint32_t w2 = c2;  // (c - P) mod Zc in half-word units
-    if constexpr (back2 != 0) { const uint32_t t = c2 + back2; w2 = min(t, t - Z2); }
-    const float2 m = *reinterpret_cast<const float2 *>(th.smem + (C::off_mags + i * C::ZC * 8) + w2 * 4);
-    uint32_t bits;
-    if constexpr (WIDE) bits = *reinterpret_cast<const uint32_t *>(th.smem + (C::off_bw + i * C::ZC * 4) + w2 * 2);
-    else bits = *reinterpret_cast<const uint16_t *>(th.smem + (C::off_bn + i * C::ZC * 2) + w2);
-    constexpr int SH = WIDE ? 24 : 12;
-    constexpr uint32_t IDXMASK = WIDE ? 0x1f000000u : 0xf000u;
-    const bool isidx = ((bits ^ ((uint32_t)k << SH)) & IDXMASK) == 0;
-    acc = __fadd_rn(acc, record_lr(m, isidx, bits << (31 - (DEGI - 1 - k))));
-}
-
-template <class C, int J, int... Nn>
-__device__ __forceinline__ void vn_entries_s(float &acc, const Th &th, uint32_t c2, std::integer_sequence<int, Nn...>)
-{
-    (vn_entry_s<C, J, Nn>(acc, th, c2), ...);
-}
-
-// One core variable of column-block J (compile time): see vn_col above.
-template <class C, int J>
-__device__ __forceinline__ void vn_col_s(Th th)
-{
-    asm volatile("" : "+r"(th.r4));  // see cn_row_s
-    float lv = 0.f;
-    if constexpr (J >= 2) lv = __fadd_rn(__ldg(th.llr + (J - 2) * C::ZC), 0.0f);
-    float acc = 0.f;
-    vn_entries_s<C, J>(acc, th, th.r4 >> 1, std::make_integer_sequence<int, C::cdeg(J)>{});
-    if (th.active) *reinterpret_cast<float *>(th.smem + J * C::ZC * 4 + th.r4) = __fadd_rn(lv, acc);
-}
-
-template <class C, int SUB, int O = 0>
-__device__ __forceinline__ void vn_pass_s(const Th &th)
-{
-    if constexpr (O < kCols<C>.n[SUB]) {
-        vn_col_s<C, kCols<C>.item[SUB][O]>(th);
-        asm volatile("" ::: "memory");
-        vn_pass_s<C, SUB, O + 1>(th);
-    }
-}
-
-// Final syndrome of row-block I with the post-loop tie rule LQ<=0 -> 1 (:134-143) + extension hard bits.
-template <class C, int I, int K>
-__device__ __forceinline__ void final_edge_s(uint32_t &synd, const Th &th)
-{
-    constexpr int e = C::G::rowptr(I) + K;
-    constexpr uint32_t P4 = 4u * C::P(e), Z4 = 4u * C::ZC, lq = 4u * C::ZC * C::G::col(e);
-    uint32_t w = th.r4;
-    if constexpr (P4 != 0) { const uint32_t t = th.r4 + P4; w = min(t, t - Z4); }
-    synd ^= (*reinterpret_cast<const float *>(th.smem + lq + w) <= 0.f) ? 1u : 0u;
-}
-template <class C, int I, int... K>
-__device__ __forceinline__ void final_edges_s(uint32_t &synd, const Th &th, std::integer_sequence<int, K...>)
-{
-    (final_edge_s<C, I, K>(synd, th), ...);
-}
-template <class C, int I>
-__device__ __forceinline__ void final_row_s(Th th, int *flag)
-{
-    asm volatile("" : "+r"(th.r4));
-    constexpr int DEG = C::deg(I), NCORE = (I >= 4) ? DEG - 1 : DEG;
-    uint32_t synd = 0;
-    final_edges_s<C, I>(synd, th, std::make_integer_sequence<int, NCORE>{});
-    if constexpr (I >= 4) {
-        const float2 m = *reinterpret_cast<const float2 *>(th.smem + (C::off_mags + I * C::ZC * 8) + 2 * th.r4);
-        const uint32_t bits = *reinterpret_cast<const uint16_t *>(th.smem + (C::off_bn + I * C::ZC * 2) + (th.r4 >> 1));
-        const float lr = record_lr(m, ((bits ^ ((uint32_t)(DEG - 1) << 12)) & 0xf000u) == 0, bits << 31);
-        const float x = __fadd_rn(__fadd_rn(__ldg(th.llr + (C::kb + I - 2) * C::ZC), 0.0f), lr);
-        const bool hb1 = x <= 0.f;
-        const uint32_t hb = __ballot_sync(0xffffffffu, hb1);
-        if (th.active && (th.r & 31) == 0)
-            reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + (th.r >> 5)] = hb;
-        synd ^= hb1 ? 1u : 0u;
-    }
-    if (th.active && synd) flag[0] = 1;
-}
-template <class C, int SUB, int O = 0>
-__device__ __forceinline__ void final_pass_s(const Th &th, int *flag)
-{
-    if constexpr (O < kRows<C>.n[SUB]) {
-        final_row_s<C, kRows<C>.item[SUB][O]>(th, flag);
-        asm volatile("" ::: "memory");
-        final_pass_s<C, SUB, O + 1>(th, flag);
-    }
-}
-
-// run PASS<SUB> for the warp's group (sub is warp-uniform)
-template <class C, bool ET, int SUB = 0>
-__device__ __forceinline__ void run_cn(int sub, const DecArgs &a, const Th &th, int *flag)
-{
-    if constexpr (SUB < C::S) {
-        if (sub == SUB) cn_pass_s<C, ET, SUB>(a, th, flag);
-        else run_cn<C, ET, SUB + 1>(sub, a, th, flag);
-    }
-}
-template <class C, int SUB = 0>
-__device__ __forceinline__ void run_vn(int sub, const Th &th)
-{
-    if constexpr (SUB < C::S) {
-        if (sub == SUB) vn_pass_s<C, SUB>(th);
-        else run_vn<C, SUB + 1>(sub, th);
-    }
-}
-template <class C, int SUB = 0>
-__device__ __forceinline__ void run_final(int sub, const Th &th, int *flag)
-{
-    if constexpr (SUB < C::S) {
-        if (sub == SUB) final_pass_s<C, SUB>(th, flag);
-        else run_final<C, SUB + 1>(sub, th, flag);
-    }
-}
-
-template <class C, bool ET>
-__global__ void __launch_bounds__(C::nwarps * 32, 1)
-decode_spec_kernel(const __grid_constant__ DecArgs a)
-{
-    extern __shared__ __align__(16) char smem[];
-    __shared__ int s_flag[2];
-    constexpr int NT = C::nwarps * 32, ZC = C::ZC;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __reduce_min_sync(0xffffffffu, tid >> 5);
-    const int cb = blockIdx.x;  // one codeblock per CTA
-    const int colm = warp % C::tiles, sub = warp / C::tiles;
-    Th th;
-    th.smem = smem;
-    th.r = colm * 32 + lane;
-    th.r4 = (uint32_t)th.r * 4u;
-    th.llr = a.llr + (size_t)cb * C::N + th.r;
-    th.active = true;
-
-    // ---- init: records = 0 (Lr = 0, :101), LQ = LLRin (:94) with the punctured columns at 0 (:43)
-    for (int t = tid; t < C::slot_bytes / 4; t += NT) reinterpret_cast<uint32_t *>(smem)[t] = 0;
-    if (tid < 2) s_flag[tid] = 0;
-    __syncthreads();
-    for (int j = 2 + sub; j < C::ncore; j += C::S)
-        *reinterpret_cast<float *>(smem + j * ZC * 4 + th.r4) = __fadd_rn(__ldg(th.llr + (j - 2) * ZC), 0.0f);
-    __syncthreads();
-
-    bool et_done = false;
-    int it = 0;
-    for (; it < a.max_iter; ++it) {
-        int *flag = &s_flag[it & 1];
-        run_cn<C, ET>(sub, a, th, flag);
-        __syncthreads();
-        if (ET) {
-            if (*flag == 0) { et_done = true; break; }  // all parity checks hold for the current decisions (:111-114)
-            if (tid == 0) s_flag[(it + 1) & 1] = 0;
-        }
-        run_vn<C>(sub, th);
-        __syncthreads();
-    }
-    bool ok = et_done;
-    if (!et_done) {
-        int *flag = &s_flag[it & 1];
-        run_final<C>(sub, th, flag);
-        __syncthreads();
-        ok = (*flag == 0);
-    }
-
-    // ---- outputs
-    if (tid == 0) {
-        if (a.status) a.status[cb] = ok ? 1 : 0;
-        if (a.iters) a.iters[cb] = it;
-    }
-    const float *LQ = reinterpret_cast<const float *>(smem);
-    const uint32_t *ext = reinterpret_cast<const uint32_t *>(smem + C::off_ext);
-    if (a.ck) {
-        int8_t *out = a.ck + (size_t)cb * C::Nfull;
-        constexpr int ncoreN = C::ncore * ZC;
-        for (int n = tid; n < C::Nfull; n += NT) {
-            int bit;
-            if (n < ncoreN) {
-                const float x = LQ[n];
-                bit = et_done ? (x < 0.f) : (x <= 0.f);
-            } else {
-                const int m = n - ncoreN, i4 = m / ZC, r = m - i4 * ZC;
-                bit = (ext[i4 * C::tiles + (r >> 5)] >> (r & 31)) & 1u;
-            }
-            out[n] = (int8_t)bit;
-        }
-    }
-    if (a.info) {
-        constexpr int nwords = (C::K + 31) / 32;
-        for (int w = (tid >> 5); w < nwords; w += C::nwarps) {
-            const int n = 32 * w + lane;
-            bool bit = false;
-            if (n < C::K) { const float x = LQ[n]; bit = et_done ? (x < 0.f) : (x <= 0.f); }
-            const uint32_t word = __ballot_sync(0xffffffffu, bit);
-            if (lane == 0) a.info[(size_t)cb * nwords + w] = word;
-        }
-    }
-}
-
-template <class C>
-int launch_spec(const DecTab &T, const DecArgs &a, int early_term, cudaStream_t s)
-{
-    // the compile-time layout must be the one the generic tables describe
-    if (T.G != 1 || T.off_mags != C::off_mags || T.off_bw != C::off_bw || T.off_bn != C::off_bn ||
-        T.off_ext != C::off_ext || T.slot_bytes != C::slot_bytes || T.N != C::N || T.nwarps != C::nwarps) {
-        set_error("decode_minsum: specialised kernel layout mismatch");
-        return NRLDPC_EINVAL;
-    }
-    auto launch = [&](auto kern) -> int {
-        NRLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::slot_bytes));
-        kern<<<a.B, C::nwarps * 32, C::slot_bytes, s>>>(a);
-        NRLDPC_CUDA(cudaGetLastError());
-        return NRLDPC_OK;
-    };
-    return early_term ? launch(decode_spec_kernel<C, true>) : launch(decode_spec_kernel<C, false>);
-}
-
-}  // namespace spec
-
 }  // namespace
 
 int decode_minsum_geometry(const QcCfg &cfg, int *G_out, int *threads, int *smem)
 {
+    if (!std::getenv("NRLDPC_NO_SPEC") && decode_spec_geometry(cfg.bgn, cfg.Zc, threads, smem)) {
+        if (G_out) *G_out = 1;
+        return NRLDPC_OK;
+    }
     const DecTab *T = get_dec_tab(cfg);
     if (!T) return NRLDPC_EINVAL;
     if (G_out) *G_out = T->G;
@@ -957,7 +531,9 @@ int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_it
     a.ck = d_ck; a.info = d_info; a.status = d_status; a.iters = d_iters;
     static const bool no_spec = std::getenv("NRLDPC_NO_SPEC") != nullptr;  // tests: force the generic kernel
     if (!no_spec) {
-        if (cfg.bgn == 1 && cfg.Zc == 384) return spec::launch_spec<spec::Code<1, 384>>(*T, a, early_term, s);
+        bool handled = false;
+        const int rc = launch_decode_spec(cfg.bgn, cfg.Zc, a, early_term, s, &handled);
+        if (handled) return rc;
     }
     const int grid = (B + T->G - 1) / T->G, nt = T->nwarps * 32, smem = T->smem_bytes;
     auto launch = [&](auto kern) -> int {
