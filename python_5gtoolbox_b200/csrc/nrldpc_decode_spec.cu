@@ -27,6 +27,9 @@ namespace nrldpc {
 namespace {
 
 constexpr int kMaxS = 16;  // warp groups per r-tile
+#ifndef NRLDPC_PF_SUM
+#define NRLDPC_PF_SUM 16  // prefetch the next check row's inputs when deg(current) + deg(next) <= this (registers)
+#endif
 
 template <int BGN> struct Graph;
 template <> struct Graph<1> {
@@ -83,14 +86,15 @@ template <int BGN, int ZC_> struct Code {
     static constexpr uint32_t idx_mask(int i) { return kind(i) == 2 ? 0x1f000000u : (kind(i) == 1 ? 0xf000u : 0xe0u); }
     // shared-memory layout (bytes)
     static constexpr int off_lq = 0;                                          // float LQ[ncore][LQS]
-    static constexpr int off_mags = off_lq + ncore * LQS * 4;                 // float2 mags[nrows][LQS]
-    static constexpr int off_b32 = off_mags + nrows * LQS * 8;                // uint32 [count(2)][LQS]
+    static constexpr int off_mags = off_lq + ncore * LQS * 4;                 // float mag1[nrows][LQS], then mag2[nrows][LQS]
+    static constexpr int mag2_dist = nrows * LQS * 4;                         // bytes from a row's mag1 to its mag2 (multiple of 128: same banks)
+    static constexpr int off_b32 = off_mags + 2 * mag2_dist;                  // uint32 [count(2)][LQS]
     static constexpr int off_b16 = off_b32 + count(2) * LQS * 4;              // uint16 pairs of rows interleaved
     static constexpr int off_b8 = off_b16 + ((count(1) + 1) / 2) * LQS * 4;   // uint8 quads of rows interleaved
     static constexpr int off_ext = off_b8 + ((count(0) + 3) / 4) * LQS * 4;   // packed hard bits of the extension columns
     static constexpr int smem_bytes = off_ext + (nrows - 4) * tiles * 4;
     static constexpr int lq_base(int j) { return off_lq + j * LQS * 4; }
-    static constexpr int mags_base(int i) { return off_mags + i * LQS * 8; }
+    static constexpr int mags_base(int i) { return off_mags + i * LQS * 4; }  // mag1 of check 0; mag2 sits mag2_dist further
     static constexpr int bits_base(int i)  // the word of check r sits at bits_base(i) + 4 r
     {
         return kind(i) == 2 ? off_b32 + rank(i) * LQS * 4
@@ -135,6 +139,7 @@ template <class C> struct Th {  // per-thread constants
     char *smem;                 // the CTA's codeblock state
     const float *llr;           // this thread's codeblock LLR row, already offset by r
     uint32_t r4;                // r * 4
+    uint32_t r4m2;              // r * 4 + mag2_dist
     int r, tile;
     int w4[C::tiles + 1];       // warp-uniform wrap offsets in bytes of a 4-byte-stride array: w4[t] = tile >= t ? -4 Zc : 0
 };
@@ -163,14 +168,45 @@ template <class C, int E> __device__ __forceinline__ float load_lq_rot(const Th<
     return *reinterpret_cast<const float *>(th.smem + (C::lq_base(C::G::col(E)) + 4 * P) + th.r4 + th.w4[t]);
 }
 
+// What a check row reads from shared memory: its record and the posteriors of its core variables.
+template <class C, int I> struct RowIn {
+    static constexpr int NC = (I >= 4) ? C::deg(I) - 1 : C::deg(I);
+    float2 m;
+    uint32_t bits;
+    float x[NC];
+};
+template <class C, int I, int... K>
+__device__ __forceinline__ void load_row_x(RowIn<C, I> &in, const Th<C> &th, std::integer_sequence<int, K...>)
+{
+    ((in.x[K] = load_lq_rot<C, C::G::rowptr(I) + K>(th)), ...);
+}
+// r4 (+ the uniform wrap offset) must not be folded into per-lane registers hoisted out of the iteration
+// loop: the sum is made opaque here so that the wrap offsets stay in uniform registers (LDS [R + UR + imm]).
+template <class C> __device__ __forceinline__ Th<C> opaque(Th<C> th)
+{
+    asm volatile("" : "+r"(th.r4), "+r"(th.r4m2));
+    return th;
+}
+
+template <class C, int I> __device__ __forceinline__ RowIn<C, I> load_row(const Th<C> &th_)
+{
+    const Th<C> th = opaque(th_);
+    RowIn<C, I> in;
+    in.m.x = *reinterpret_cast<const float *>(th.smem + C::mags_base(I) + th.r4);
+    in.m.y = *reinterpret_cast<const float *>(th.smem + (C::mags_base(I) + C::mag2_dist) + th.r4);
+    in.bits = load_bits<C, I>(th.smem + C::bits_base(I) + th.r4);
+    load_row_x<C, I>(in, th, std::make_integer_sequence<int, RowIn<C, I>::NC>{});
+    return in;
+}
+
 template <class C, int I, int K, bool ET>
 __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, float &m2, uint32_t &synd, const Th<C> &th,
-                                          float2 m, uint32_t bits, uint32_t idxf, float llr_e)
+                                          const RowIn<C, I> &in, uint32_t idxf, float llr_e)
 {
-    constexpr int DEG = C::deg(I), e = C::G::rowptr(I) + K;
+    constexpr int DEG = C::deg(I);
     constexpr bool EXT = I >= 4;
     const bool isidx = idxf == ((uint32_t)K << C::idx_shift(I));
-    const float lr = record_lr(m, isidx, bits << (31 - (DEG - 1 - K)));
+    const float lr = record_lr(in.m, isidx, in.bits << (31 - (DEG - 1 - K)));
     float x;
     if constexpr (EXT && K == DEG - 1) {
         x = __fadd_rn(llr_e, lr);  // posterior of the degree-1 extension variable (:126)
@@ -179,7 +215,7 @@ __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, floa
             if ((th.r & 31) == 0) reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + th.tile] = hb;
         }
     } else {
-        x = load_lq_rot<C, e>(th);
+        x = in.x[K];
     }
     if constexpr (ET) synd ^= __float_as_uint(x);  // sign bit = hard decision LQ<0 (:107-108)
     q[K] = __fsub_rn(x, lr);                        // Lq = LQ - Lr (:131)
@@ -189,49 +225,50 @@ __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, floa
 
 template <class C, int I, bool ET, int... K>
 __device__ __forceinline__ void cn_edges_s(float (&q)[C::deg(I)], float &m1, float &m2, uint32_t &synd, const Th<C> &th,
-                                           float2 m, uint32_t bits, uint32_t idxf, float llr_e,
+                                           const RowIn<C, I> &in, uint32_t idxf, float llr_e,
                                            std::integer_sequence<int, K...>)
 {
-    (cn_edge_s<C, I, K, ET>(q, m1, m2, synd, th, m, bits, idxf, llr_e), ...);
+    (cn_edge_s<C, I, K, ET>(q, m1, m2, synd, th, in, idxf, llr_e), ...);
 }
 
 // One check row of row-block I (compile time), lifted index r: syndrome bit of the current hard
 // decisions, then the min-sum update of its record from Lq = LQ - Lr_old
 // (py5gphy/ldpc/nr_ldpc_decode.py:107-123, :178-227).
 template <class C, int I, bool ET, bool B0>
-__device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int *flag, const float llr_e)
+__device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int *flag, const RowIn<C, I> &in,
+                                         const float llr_e)
 {
     constexpr int DEG = C::deg(I);
-    char *rec = th.smem + C::mags_base(I) + 2 * th.r4;
+    char *rec = th.smem + C::mags_base(I) + th.r4;
     char *bp = th.smem + C::bits_base(I) + th.r4;
-    const float2 m = *reinterpret_cast<const float2 *>(rec);
-    const uint32_t bits = load_bits<C, I>(bp);
-    const uint32_t idxf = bits & C::idx_mask(I);
+    const uint32_t idxf = in.bits & C::idx_mask(I);
     float q[DEG];
     float m1 = __uint_as_float(kInfBits), m2 = m1;
     uint32_t synd = 0;
-    cn_edges_s<C, I, ET>(q, m1, m2, synd, th, m, bits, idxf, llr_e, std::make_integer_sequence<int, DEG>{});
+    cn_edges_s<C, I, ET>(q, m1, m2, synd, th, in, idxf, llr_e, std::make_integer_sequence<int, DEG>{});
     // signs of Lq and the argmin: an edge is "hot" when |Lq| == min1, i.e. min1 - |Lq| is +0 (never NaN
     // for finite inputs).  Edges that tie at min1 make min2 == min1, so any hot edge may carry the index.
     uint32_t sacc = 0, cold = 0;
 #pragma unroll
     for (int k = 0; k < DEG; ++k) {
-        sacc = push_top_bit(sacc, __float_as_uint(q[k]));                            // sign of Lq on edge k -> bit DEG-1-k
+        sacc = push_top_bit(sacc, __float_as_uint(q[k]));                               // sign of Lq on edge k -> bit DEG-1-k
         cold = push_top_bit(cold, __float_as_uint(__fsub_rn(fabsf(m1), fabsf(q[k]))));  // 1 when |Lq| > min1
     }
     constexpr uint32_t ALL = (1u << DEG) - 1u;
     const uint32_t hot = ~cold & ALL;
-    const uint32_t kmin = (uint32_t)(DEG - 32) + (uint32_t)__clz(hot);              // DEG-1 - (31 - clz): smallest hot k
+    const uint32_t kmin = (uint32_t)(DEG - 32) + (uint32_t)__clz(hot);  // DEG-1 - (31 - clz): smallest hot k
     // :199-202  Lr = alpha * sign_prod * sign(Lq) * max(minv - beta, 0), minv = min2 on the argmin edge
     // (beta == 0: max(m - 0, 0) == m for m >= +0)
     const float mag1 = B0 ? __fmul_rn(a.alpha, fabsf(m1)) : __fmul_rn(a.alpha, fmaxf(__fsub_rn(fabsf(m1), a.beta), 0.f));
     const float mag2 = B0 ? __fmul_rn(a.alpha, m2) : __fmul_rn(a.alpha, fmaxf(__fsub_rn(m2, a.beta), 0.f));
-    const uint32_t sp = (uint32_t)((int)__float_as_uint(m1) >> 31);                   // all ones when the sign product is -
+    const uint32_t sp = (uint32_t)((int)__float_as_uint(m1) >> 31);  // all ones when the sign product is -
     const uint32_t nb = ((sacc ^ sp) & ALL) | (kmin << C::idx_shift(I));
-    *reinterpret_cast<float2 *>(rec) = make_float2(mag1, mag2);
+    *reinterpret_cast<float *>(rec) = mag1;
+    *reinterpret_cast<float *>(rec + C::mag2_dist) = mag2;
     store_bits<C, I>(bp, nb);
     if (th.tile == 0) {  // mirror of the first 32 records behind the array (rotated reads of the variable pass)
-        *reinterpret_cast<float2 *>(rec + C::ZC * 8) = make_float2(mag1, mag2);
+        *reinterpret_cast<float *>(rec + C::ZC * 4) = mag1;
+        *reinterpret_cast<float *>(rec + C::mag2_dist + C::ZC * 4) = mag2;
         store_bits<C, I>(bp + C::ZC * 4, nb);
     }
     if (ET && (synd >> 31)) flag[0] = 1;
@@ -244,17 +281,29 @@ template <class C, int I> __device__ __forceinline__ float load_ext_llr(const Th
     else return 0.f;
 }
 
-// The rows of warp group SUB, one after the other; the LLR a row needs is fetched (from L2) while the
-// previous row is being processed.
+// The rows of warp group SUB, software-pipelined: the compiler cannot move a row's shared-memory loads
+// above the previous row's record stores (it cannot prove they do not alias), so the next row's inputs
+// are loaded, in program order, BEFORE the current row is computed and stored; its channel LLR (L2) too.
+// Rows whose combined degree exceeds NRLDPC_PF_SUM load their inputs after the store instead (registers).
 template <class C, bool ET, bool B0, int SUB, int O = 0>
-__device__ __forceinline__ void cn_pass_s(const DecArgs &a, const Th<C> &th, int *flag, const float llr_cur)
+__device__ __forceinline__ void cn_pass_s(const DecArgs &a, const Th<C> &th, int *flag,
+                                          const RowIn<C, kRows<C>.item[SUB][O]> &in_cur, const float llr_cur)
 {
-    if constexpr (O < kRows<C>.n[SUB]) {
-        float llr_nxt = 0.f;
-        if constexpr (O + 1 < kRows<C>.n[SUB]) llr_nxt = load_ext_llr<C, kRows<C>.item[SUB][O + 1]>(th);
-        cn_row_s<C, kRows<C>.item[SUB][O], ET, B0>(a, th, flag, llr_cur);
-        asm volatile("" ::: "memory");  // keep the rows' loads from being hoisted across each other (register pressure)
-        cn_pass_s<C, ET, B0, SUB, O + 1>(a, th, flag, llr_nxt);
+    constexpr int I = kRows<C>.item[SUB][O];
+    if constexpr (O + 1 < kRows<C>.n[SUB]) {
+        constexpr int In = kRows<C>.item[SUB][O + 1];
+        const float llr_nxt = load_ext_llr<C, In>(th);
+        if constexpr (C::deg(I) + C::deg(In) <= NRLDPC_PF_SUM) {
+            const RowIn<C, In> in_nxt = load_row<C, In>(th);
+            cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
+            cn_pass_s<C, ET, B0, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
+        } else {
+            cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
+            const RowIn<C, In> in_nxt = load_row<C, In>(th);
+            cn_pass_s<C, ET, B0, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
+        }
+    } else {
+        cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
     }
 }
 
@@ -263,10 +312,11 @@ __device__ __forceinline__ void vn_entry_s(float &acc, const Th<C> &th)
 {
     constexpr int e = C::cedge(J, Nn), i = C::row_of(e), k = e - C::G::rowptr(i), DEGI = C::deg(i);
     constexpr int back = (C::ZC - C::P(e)) % C::ZC, t = C::wrap_tile(back);  // check r = (c - P) mod Zc
-    const float2 m = *reinterpret_cast<const float2 *>(th.smem + (C::mags_base(i) + 8 * back) + 2 * th.r4 + 2 * th.w4[t]);
     const uint32_t bits = load_bits<C, i>(th.smem + (C::bits_base(i) + 4 * back) + th.r4 + th.w4[t]);
     const bool isidx = ((bits ^ ((uint32_t)k << C::idx_shift(i))) & C::idx_mask(i)) == 0;
-    acc = __fadd_rn(acc, record_lr(m, isidx, bits << (31 - (DEGI - 1 - k))));
+    // only the magnitude this edge uses is read (one 128-byte wavefront): mag2 on the argmin edge, mag1 elsewhere
+    const float mag = *reinterpret_cast<const float *>(th.smem + (C::mags_base(i) + 4 * back) + (isidx ? th.r4m2 : th.r4) + th.w4[t]);
+    acc = __fadd_rn(acc, __uint_as_float(__float_as_uint(mag) ^ ((bits << (31 - (DEGI - 1 - k))) & 0x80000000u)));
 }
 
 template <class C, int J, int... Nn>
@@ -278,11 +328,16 @@ __device__ __forceinline__ void vn_entries_s(float &acc, const Th<C> &th, std::i
 // One core variable of column-block J (compile time), lifted index c = r: LQ = LLRin + sum_i Lr(i) in
 // ascending row-block order = ascending check index (py5gphy/ldpc/nr_ldpc_decode.py:126).
 template <class C, int J>
-__device__ __forceinline__ void vn_col_s(const Th<C> &th, const float lv)
+__device__ __forceinline__ float vn_col_s(const Th<C> &th_, const float lv)
 {
+    const Th<C> th = opaque(th_);
     float acc = 0.f;
     vn_entries_s<C, J>(acc, th, std::make_integer_sequence<int, C::cdeg(J)>{});
-    const float lq = __fadd_rn(lv, acc);
+    return __fadd_rn(lv, acc);
+}
+template <class C, int J>
+__device__ __forceinline__ void vn_store_s(const Th<C> &th, const float lq)
+{
     float *dst = reinterpret_cast<float *>(th.smem + C::lq_base(J) + th.r4);
     *dst = lq;
     if (th.tile == 0) dst[C::ZC] = lq;  // mirror for the rotated reads of the check pass
@@ -295,15 +350,19 @@ template <class C, int J> __device__ __forceinline__ float load_col_llr(const Th
     else return 0.f;
 }
 
+// The columns of warp group SUB.  A column's posterior is stored after the NEXT column's records have
+// been read (same aliasing argument as in cn_pass_s), its channel LLR is fetched one column ahead.
 template <class C, int SUB, int O = 0>
-__device__ __forceinline__ void vn_pass_s(const Th<C> &th, const float lv_cur)
+__device__ __forceinline__ void vn_pass_s(const Th<C> &th, const float lv_cur, const float lq_prev)
 {
     if constexpr (O < kCols<C>.n[SUB]) {
         float lv_nxt = 0.f;
         if constexpr (O + 1 < kCols<C>.n[SUB]) lv_nxt = load_col_llr<C, kCols<C>.item[SUB][O + 1]>(th);
-        vn_col_s<C, kCols<C>.item[SUB][O]>(th, lv_cur);
-        asm volatile("" ::: "memory");
-        vn_pass_s<C, SUB, O + 1>(th, lv_nxt);
+        const float lq = vn_col_s<C, kCols<C>.item[SUB][O]>(th, lv_cur);
+        if constexpr (O > 0) vn_store_s<C, kCols<C>.item[SUB][O - 1]>(th, lq_prev);
+        vn_pass_s<C, SUB, O + 1>(th, lv_nxt, lq);
+    } else if constexpr (O > 0) {
+        vn_store_s<C, kCols<C>.item[SUB][O - 1]>(th, lq_prev);
     }
 }
 
@@ -320,7 +379,9 @@ __device__ __forceinline__ void final_row_s(const Th<C> &th, int *flag)
     uint32_t synd = 0;
     final_edges_s<C, I>(synd, th, std::make_integer_sequence<int, NCORE>{});
     if constexpr (I >= 4) {
-        const float2 m = *reinterpret_cast<const float2 *>(th.smem + C::mags_base(I) + 2 * th.r4);
+        float2 m;
+        m.x = *reinterpret_cast<const float *>(th.smem + C::mags_base(I) + th.r4);
+        m.y = *reinterpret_cast<const float *>(th.smem + (C::mags_base(I) + C::mag2_dist) + th.r4);
         const uint32_t bits = load_bits<C, I>(th.smem + C::bits_base(I) + th.r4);
         const bool isidx = ((bits ^ ((uint32_t)(DEG - 1) << C::idx_shift(I))) & C::idx_mask(I)) == 0;
         const float lr = record_lr(m, isidx, bits << 31);
@@ -347,7 +408,7 @@ template <class C, bool ET, bool B0, int SUB = 0>
 __device__ __forceinline__ void run_cn(int sub, const DecArgs &a, const Th<C> &th, int *flag)
 {
     if constexpr (SUB < C::S) {
-        if (sub == SUB) cn_pass_s<C, ET, B0, SUB>(a, th, flag, load_ext_llr<C, kRows<C>.item[SUB][0]>(th));
+        if (sub == SUB) cn_pass_s<C, ET, B0, SUB>(a, th, flag, load_row<C, kRows<C>.item[SUB][0]>(th), load_ext_llr<C, kRows<C>.item[SUB][0]>(th));
         else run_cn<C, ET, B0, SUB + 1>(sub, a, th, flag);
     }
 }
@@ -355,7 +416,7 @@ template <class C, int SUB = 0>
 __device__ __forceinline__ void run_vn(int sub, const Th<C> &th)
 {
     if constexpr (SUB < C::S) {
-        if (sub == SUB) vn_pass_s<C, SUB>(th, load_col_llr<C, kCols<C>.item[SUB][0]>(th));
+        if (sub == SUB) vn_pass_s<C, SUB>(th, load_col_llr<C, kCols<C>.item[SUB][0]>(th), 0.f);
         else run_vn<C, SUB + 1>(sub, th);
     }
 }
@@ -384,6 +445,7 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     th.tile = warp % C::tiles;
     th.r = th.tile * 32 + lane;
     th.r4 = (uint32_t)th.r * 4u;
+    th.r4m2 = th.r4 + (uint32_t)C::mag2_dist;
     th.llr = a.llr + (size_t)cb * C::N + th.r;
 #pragma unroll
     for (int t = 0; t <= C::tiles; ++t) th.w4[t] = (th.tile >= t) ? -4 * ZC : 0;

@@ -6,7 +6,10 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
-from python_5gtoolbox_b200 import engine  # noqa: E402
+from python_5gtoolbox_b200 import _lib, engine  # noqa: E402
+
+if os.environ.get("NRLDPC_SO"):  # kernel experiments: time an alternative build of the library
+    _lib.SO_PATH = os.path.abspath(os.environ["NRLDPC_SO"])
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
