@@ -81,7 +81,7 @@ def cpu_reference_run(steps, warmup, sample_cbs=None, early_term=0):
     from oracle import oracle as O
     O.build()
     threads = O.num_threads()
-    n = sample_cbs or max(threads * 4, 16)
+    n = sample_cbs or max(threads * 100, 64)   # ~26 ms per codeblock per core -> a few seconds per step
     rng = np.random.default_rng(0x5601)
     ck = rng.integers(0, 2, (n, K_INFO)).astype("i1")
     dn = O.encode_batch(ck, BGN, ZC)
@@ -228,13 +228,14 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": TRAFFIC_BYTES_PER_CB * B, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_CB,
-                         "kernel": "decode_minsum_kernel", "kernel_ms": ms / args.steps,
-                         "note": "HBM is not the binding roof of this kernel (10 on-chip iterations per byte); "
-                                 "see DESIGN.md for the issue-slot / shared-memory roof"},
+                         "kernel": "decode_spec_kernel<Code<1,384>,ET=0,B0=1>", "kernel_ms": ms / args.steps,
+                         "note": "HBM is not the binding roof of this kernel (10 on-chip iterations per byte): the check "
+                                 "pass is bound by the SM ALU pipe / issue slots, the variable pass by shared-memory "
+                                 "wavefronts; see DESIGN.md and profiles/"},
             "clocks": clk.summary(),
         }
         if not args.no_cpu:
-            gbps, threads, n, sps = cpu_reference_run(1, 0)
+            gbps, threads, n, sps = cpu_reference_run(1, 0, sample_cbs=max(400 * (os.cpu_count() or 1), 256))  # ~10 s of CPU work
             out["cpu_baseline"] = {"value": gbps, "unit": "Gbit/s", "cores": threads, "kind": "port",
                                    "sample": f"{n} codeblocks of the same workload, float64 C port of the reference (oracle/), "
                                              f"{threads} OpenMP threads, {sps:.2f} s"}
@@ -249,8 +250,8 @@ def ctypes_int():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per codeblock from the committed `ncu --set full` capture
-# (profiles/r1_decode_minsum_ncu_summary.md: 60.07 MB + 0.38 MB for 592 codeblocks)
-TRAFFIC_BYTES_PER_CB = (60069376 + 384000) / 592
+# (profiles/r1_decode_spec_ncu_summary.md: 60.160 MB + 0.362 MB for 592 codeblocks)
+TRAFFIC_BYTES_PER_CB = (60160000 + 361728) / 592
 
 
 def main():

@@ -15,6 +15,7 @@
 //     (min1 - |Lq|) computed on the FMA pipe, instead of a compare + select per edge;
 //   * sign/argmin words are 8-bit for rows of degree <= 5, 16-bit up to degree 12 and 32-bit above,
 //     interleaved so that all of them have a 4-byte stride (one set of wrap offsets, no bank conflicts).
+#include <algorithm>
 #include <cstdlib>
 #include <utility>
 
@@ -27,6 +28,9 @@ namespace nrldpc {
 namespace {
 
 constexpr int kMaxS = 16;  // warp groups per r-tile
+#ifndef NRLDPC_SIGN_FMA
+#define NRLDPC_SIGN_FMA 0
+#endif
 #ifndef NRLDPC_PF_SUM
 #define NRLDPC_PF_SUM 16  // prefetch the next check row's inputs when deg(current) + deg(next) <= this (registers)
 #endif
@@ -248,12 +252,27 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
     cn_edges_s<C, I, ET>(q, m1, m2, synd, th, in, idxf, llr_e, std::make_integer_sequence<int, DEG>{});
     // signs of Lq and the argmin: an edge is "hot" when |Lq| == min1, i.e. min1 - |Lq| is +0 (never NaN
     // for finite inputs).  Edges that tie at min1 make min2 == min1, so any hot edge may carry the index.
+#if NRLDPC_SIGN_FMA
+    // Sign word on the FMA pipe (the check pass is bound by the ALU pipe): [Lq < 0] = sat(Lq * -inf)
+    // exactly -- -inf/+inf saturate to 0/1 and 0 * inf = NaN saturates to +0 -- accumulated as an exact
+    // small integer on top of 2^23, whose mantissa then holds the word.
+    uint32_t cold = 0;
+    float saccf = 8388608.0f;
+#pragma unroll
+    for (int k = 0; k < DEG; ++k) {
+        const float neg = __saturatef(__fmul_rn(q[k], __uint_as_float(0xff800000u)));
+        saccf = __fmaf_rn(neg, (float)(1u << (DEG - 1 - k)), saccf);                      // sign of Lq on edge k -> bit DEG-1-k
+        cold = push_top_bit(cold, __float_as_uint(__fsub_rn(fabsf(m1), fabsf(q[k]))));  // 1 when |Lq| > min1
+    }
+    const uint32_t sacc = __float_as_uint(saccf);
+#else
     uint32_t sacc = 0, cold = 0;
 #pragma unroll
     for (int k = 0; k < DEG; ++k) {
         sacc = push_top_bit(sacc, __float_as_uint(q[k]));                               // sign of Lq on edge k -> bit DEG-1-k
         cold = push_top_bit(cold, __float_as_uint(__fsub_rn(fabsf(m1), fabsf(q[k]))));  // 1 when |Lq| > min1
     }
+#endif
     constexpr uint32_t ALL = (1u << DEG) - 1u;
     const uint32_t hot = ~cold & ALL;
     const uint32_t kmin = (uint32_t)(DEG - 32) + (uint32_t)__clz(hot);  // DEG-1 - (31 - clz): smallest hot k
@@ -429,6 +448,22 @@ __device__ __forceinline__ void run_final(int sub, const Th<C> &th, int *flag)
     }
 }
 
+// Pull `bytes` (a multiple of 16) at a 16-byte aligned global address into L2, asynchronously.
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+int num_sms()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <class C, bool ET, bool B0>
 __global__ void __launch_bounds__(C::nwarps * 32, 1)
 decode_spec_kernel(const __grid_constant__ DecArgs a)
@@ -438,7 +473,6 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     constexpr int NT = C::nwarps * 32, ZC = C::ZC;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __reduce_min_sync(0xffffffffu, tid >> 5);  // warp-uniform (REDUX writes a uniform register)
-    const int cb = blockIdx.x;  // one codeblock per CTA
     const int sub = warp / C::tiles;
     Th<C> th;
     th.smem = smem;
@@ -446,68 +480,87 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     th.r = th.tile * 32 + lane;
     th.r4 = (uint32_t)th.r * 4u;
     th.r4m2 = th.r4 + (uint32_t)C::mag2_dist;
-    th.llr = a.llr + (size_t)cb * C::N + th.r;
 #pragma unroll
     for (int t = 0; t <= C::tiles; ++t) th.w4[t] = (th.tile >= t) ? -4 * ZC : 0;
 
-    // ---- init: records = 0 (Lr = 0, :101), LQ = LLRin (:94) with the punctured columns at 0 (:43)
-    for (int t = tid; t < C::smem_bytes / 4; t += NT) reinterpret_cast<uint32_t *>(smem)[t] = 0;
-    if (tid < 2) s_flag[tid] = 0;
-    __syncthreads();
-    for (int j = 2 + sub; j < C::ncore; j += C::S) {
-        const float v = __fadd_rn(__ldg(th.llr + (j - 2) * ZC), 0.0f);  // -0.0 -> +0.0
-        float *dst = reinterpret_cast<float *>(smem + C::lq_base(j) + th.r4);
-        *dst = v;
-        if (th.tile == 0) dst[ZC] = v;
-    }
-    __syncthreads();
+    // Persistent CTA (one per SM: the codeblock state fills shared memory): codeblocks blockIdx.x,
+    // blockIdx.x + gridDim.x, ...  The channel LLRs are read straight from global memory every iteration
+    // (L2 hits); the NEXT codeblock's row is pulled into L2 while the current one is decoded, so that no
+    // HBM latency is exposed at a codeblock boundary.
+    const bool pf = tid == 0 && (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0;  // bulk prefetch needs 16-byte alignment
+    if (pf) prefetch_l2(a.llr + (size_t)blockIdx.x * C::N, C::N * 4);
+    for (int cb = blockIdx.x; cb < a.B; cb += gridDim.x) {
+        th.llr = a.llr + (size_t)cb * C::N + th.r;
+        if (pf && cb + (int)gridDim.x < a.B) prefetch_l2(a.llr + (size_t)(cb + gridDim.x) * C::N, C::N * 4);
 
-    bool et_done = false;
-    int it = 0;
-    for (; it < a.max_iter; ++it) {
-        int *flag = &s_flag[it & 1];
-        run_cn<C, ET, B0>(sub, a, th, flag);
-        __syncthreads();
-        if (ET) {
-            if (*flag == 0) { et_done = true; break; }  // all parity checks hold for the current decisions (:111-114)
-            if (tid == 0) s_flag[(it + 1) & 1] = 0;
+        // ---- init: records = 0 (Lr = 0, :101), LQ = LLRin (:94) with the punctured columns at 0 (:43)
+        {
+            constexpr int z0 = C::off_mags / 16, z1 = C::smem_bytes / 16;
+            static_assert(C::off_mags % 16 == 0 && C::smem_bytes % 16 == 0, "16-byte zero fill");
+            for (int t = z0 + tid; t < z1; t += NT) reinterpret_cast<uint4 *>(smem)[t] = make_uint4(0, 0, 0, 0);
+            for (int t = tid; t < 2 * C::LQS; t += NT) reinterpret_cast<float *>(smem + C::lq_base(0))[t] = 0.f;
+            if (tid < 2) s_flag[tid] = 0;
+            for (int j = 2 + sub; j < C::ncore; j += C::S) {
+                const float v = __fadd_rn(__ldg(th.llr + (j - 2) * ZC), 0.0f);  // -0.0 -> +0.0
+                float *dst = reinterpret_cast<float *>(smem + C::lq_base(j) + th.r4);
+                *dst = v;
+                if (th.tile == 0) dst[ZC] = v;
+            }
         }
-        run_vn<C>(sub, th);
         __syncthreads();
-    }
-    bool ok = et_done;
-    if (!et_done) {
-        int *flag = &s_flag[it & 1];
-        run_final<C>(sub, th, flag);
-        __syncthreads();
-        ok = (*flag == 0);
-    }
 
-    // ---- outputs
-    if (tid == 0) {
-        if (a.status) a.status[cb] = ok ? 1 : 0;
-        if (a.iters) a.iters[cb] = it;
-    }
-    const uint32_t *ext = reinterpret_cast<const uint32_t *>(smem + C::off_ext);
-    if (a.ck) {
-        int8_t *out = a.ck + (size_t)cb * C::Nfull;
-        for (int j = 0; j < C::ncore; ++j) {
-            const float *LQ = reinterpret_cast<const float *>(smem + C::lq_base(j));
-            for (int c = tid; c < ZC; c += NT) out[j * ZC + c] = (int8_t)(et_done ? (LQ[c] < 0.f) : (LQ[c] <= 0.f));
+        bool et_done = false;
+        int it = 0;
+        for (; it < a.max_iter; ++it) {
+            int *flag = &s_flag[it & 1];
+#ifndef NRLDPC_EXP_NO_CN
+            run_cn<C, ET, B0>(sub, a, th, flag);
+#endif
+            __syncthreads();
+            if (ET) {
+                if (*flag == 0) { et_done = true; break; }  // all parity checks hold for the current decisions (:111-114)
+                if (tid == 0) s_flag[(it + 1) & 1] = 0;
+            }
+#ifndef NRLDPC_EXP_NO_VN
+            run_vn<C>(sub, th);
+#endif
+            __syncthreads();
         }
-        for (int n = tid; n < (C::nrows - 4) * ZC; n += NT) {
-            const int i4 = n / ZC, r = n - i4 * ZC;
-            out[C::ncore * ZC + n] = (int8_t)((ext[i4 * C::tiles + (r >> 5)] >> (r & 31)) & 1u);
+        bool ok = et_done;
+        if (!et_done) {
+            int *flag = &s_flag[it & 1];
+            run_final<C>(sub, th, flag);
+            __syncthreads();
+            ok = (*flag == 0);
         }
-    }
-    if (a.info) {
-        constexpr int nwords = C::K / 32;  // K = kb * Zc, Zc a multiple of 32
-        for (int w = (tid >> 5); w < nwords; w += C::nwarps) {
-            const int n = 32 * w + lane, j = n / ZC, c = n - j * ZC;
-            const float x = *reinterpret_cast<const float *>(smem + C::lq_base(j) + 4 * c);
-            const uint32_t word = __ballot_sync(0xffffffffu, et_done ? (x < 0.f) : (x <= 0.f));
-            if (lane == 0) a.info[(size_t)cb * nwords + w] = word;
+
+        // ---- outputs
+        if (tid == 0) {
+            if (a.status) a.status[cb] = ok ? 1 : 0;
+            if (a.iters) a.iters[cb] = it;
         }
+        const uint32_t *ext = reinterpret_cast<const uint32_t *>(smem + C::off_ext);
+        if (a.ck) {
+            int8_t *out = a.ck + (size_t)cb * C::Nfull;
+            for (int j = 0; j < C::ncore; ++j) {
+                const float *LQ = reinterpret_cast<const float *>(smem + C::lq_base(j));
+                for (int c = tid; c < ZC; c += NT) out[j * ZC + c] = (int8_t)(et_done ? (LQ[c] < 0.f) : (LQ[c] <= 0.f));
+            }
+            for (int n = tid; n < (C::nrows - 4) * ZC; n += NT) {
+                const int i4 = n / ZC, r = n - i4 * ZC;
+                out[C::ncore * ZC + n] = (int8_t)((ext[i4 * C::tiles + (r >> 5)] >> (r & 31)) & 1u);
+            }
+        }
+        if (a.info) {
+            constexpr int nwords = C::K / 32;  // K = kb * Zc, Zc a multiple of 32
+            for (int w = (tid >> 5); w < nwords; w += C::nwarps) {
+                const int n = 32 * w + lane, j = n / ZC, c = n - j * ZC;
+                const float x = *reinterpret_cast<const float *>(smem + C::lq_base(j) + 4 * c);
+                const uint32_t word = __ballot_sync(0xffffffffu, et_done ? (x < 0.f) : (x <= 0.f));
+                if (lane == 0) a.info[(size_t)cb * nwords + w] = word;
+            }
+        }
+        __syncthreads();  // the state is re-initialised for the next codeblock
     }
 }
 
@@ -517,7 +570,7 @@ int launch_spec(const DecArgs &a, int early_term, cudaStream_t s)
     static_assert(C::smem_bytes <= 227 * 1024 - 64, "codeblock state does not fit in shared memory");
     auto launch = [&](auto kern) -> int {
         NRLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
-        kern<<<a.B, C::nwarps * 32, C::smem_bytes, s>>>(a);
+        kern<<<std::min(a.B, num_sms()), C::nwarps * 32, C::smem_bytes, s>>>(a);
         NRLDPC_CUDA(cudaGetLastError());
         return NRLDPC_OK;
     };

@@ -164,6 +164,81 @@ def test_decode_all_lifting_sizes_vs_oracle(eng, oracle, bgn):
     assert diff64 <= max(0, int(tot * 1e-4)), (diff64, tot)
 
 
+def test_decode_headline_spec_kernel_vs_oracle(eng, oracle):
+    """BG1 Zc=384 goes through the compile-time specialised kernel (nrldpc_decode_spec.cu): bit-exact
+    against the fp32 restatement for NMS / OMS / mixed / plain min-sum, with and without early
+    termination, at SNRs where blocks converge early, late and not at all; a batch larger than one
+    wave of persistent CTAs; ties, zeros and -0.0 inputs."""
+    bgn, Zc = 1, 384
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    rng = np.random.default_rng(384)
+    ck = _rand_ck(rng, bgn, Zc, 40, fillers=False)
+    dn = oracle.encode_batch(ck.copy(), bgn, Zc)
+    cases = [(-3.0, 6, 0.8, 0.0, 1), (0.4, 10, 0.8, 0.0, 1), (0.4, 10, 0.8, 0.0, 0), (0.6, 12, 1.0, 0.5, 1),
+             (0.6, 9, 0.8, 0.3, 0), (1.5, 10, 1.0, 0.0, 1), (0.2, 16, 0.7, 0.0, 1)]
+    for ci, (snr, L, alpha, beta, et) in enumerate(cases):
+        sel = slice(5 * ci, 5 * ci + 10)
+        llr = _awgn(rng, dn[sel], snr)
+        r = eng.decode_batch(llr, Zc, bgn, L, alpha, beta, bool(et), want_info=True)
+        c, s, i = oracle.decode_batch(llr, Zc, bgn, L, "min-sum", alpha, beta, et, np.float32)
+        assert np.array_equal(r["ck"], c) and np.array_equal(r["status"], s) and np.array_equal(r["iters"], i), cases[ci]
+        info = np.unpackbits(r["info"].view(np.uint8), axis=1, bitorder="little")[:, :K]
+        assert np.array_equal(info, c[:, :K])
+    # exact ties / zeros / -0.0 / dyadic values (every intermediate exact, many equal magnitudes)
+    t = np.zeros((4, N), np.float32)
+    t[1, ::2] = -0.0
+    t[2] = (rng.integers(-2, 3, N) * 0.5).astype(np.float32)
+    t[3] = np.where(dn[0] == 1, -4.0, 4.0).astype(np.float32)
+    t[3, rng.integers(0, N, 900)] *= -0.5
+    for alpha, beta, et in [(0.5, 0.25, 1), (1.0, 0.0, 1), (0.75, 0.0, 0)]:
+        r = eng.decode_batch(t, Zc, bgn, 5, alpha, beta, bool(et))
+        c, s, i = oracle.decode_batch(t, Zc, bgn, 5, "min-sum", alpha, beta, et, np.float32)
+        assert np.array_equal(r["ck"], c) and np.array_equal(r["status"], s) and np.array_equal(r["iters"], i), (alpha, beta, et)
+    # more codeblocks than persistent CTAs (the kernel loops over codeblocks): replicate a small set and
+    # compare every copy with the first one
+    import torch
+    base = torch.from_numpy(_awgn(rng, dn[:8], 0.5)).cuda()
+    big = base.repeat(40, 1).contiguous()   # 320 codeblocks > 148 SMs
+    r = eng.decode_batch(big, Zc, bgn, 10, 0.8, 0.0, True)
+    torch.cuda.synchronize()
+    for key in ("ck", "status", "iters"):
+        v = r[key].reshape(40, 8, -1)
+        assert torch.equal(v, v[:1].expand_as(v)), key
+    c, s, i = oracle.decode_batch(base.cpu().numpy(), Zc, bgn, 10, "min-sum", 0.8, 0.0, 1, np.float32)
+    assert np.array_equal(r["ck"][:8].cpu().numpy(), c) and np.array_equal(r["iters"][:8].cpu().numpy(), i)
+
+
+def test_decode_spec_and_table_kernels_agree(eng):
+    """The table-driven kernel (NRLDPC_NO_SPEC=1, read once per process -> subprocess) and the
+    specialised kernel give identical outputs on the same BG1 Zc=384 batch."""
+    import os, subprocess, sys, tempfile
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, sys.argv[1])\n"
+        "from python_5gtoolbox_b200 import engine\n"
+        "llr = np.load(sys.argv[2])\n"
+        "r = engine.decode_batch(llr, 384, 1, 8, 0.8, 0.3, True)\n"
+        "np.savez(sys.argv[3], ck=r['ck'], status=r['status'], iters=r['iters'])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = np.random.default_rng(77)
+    ck = eng.random_bits(12, 22 * 384, seed=5, device="cuda")
+    dn = eng.encode_batch(ck, 1).cpu().numpy()
+    llr = _awgn(rng, dn, 0.3)
+    with tempfile.TemporaryDirectory() as d:
+        np.save(os.path.join(d, "llr.npy"), llr)
+        outs = []
+        for flag in (None, "1"):
+            env = dict(os.environ)
+            env.pop("NRLDPC_NO_SPEC", None)
+            if flag:
+                env["NRLDPC_NO_SPEC"] = flag
+            out = os.path.join(d, f"out{flag}.npz")
+            subprocess.run([sys.executable, "-c", code, root, os.path.join(d, "llr.npy"), out], check=True, env=env)
+            outs.append(np.load(out))
+    for key in ("ck", "status", "iters"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+
+
 def test_decode_fixed_iterations_and_edge_cases(eng, oracle):
     rng = np.random.default_rng(9)
     for bgn, Zc in [(1, 12), (2, 20), (1, 96)]:
