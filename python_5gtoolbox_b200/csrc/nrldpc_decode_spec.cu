@@ -28,8 +28,14 @@ namespace nrldpc {
 namespace {
 
 constexpr int kMaxS = 16;  // warp groups per r-tile
+#ifndef NRLDPC_VN_PSEL
+#define NRLDPC_VN_PSEL 1
+#endif
+#ifndef NRLDPC_SUB_INTERLEAVE
+#define NRLDPC_SUB_INTERLEAVE 0
+#endif
 #ifndef NRLDPC_SIGN_FMA
-#define NRLDPC_SIGN_FMA 0
+#define NRLDPC_SIGN_FMA 1
 #endif
 #ifndef NRLDPC_PF_SUM
 #define NRLDPC_PF_SUM 16  // prefetch the next check row's inputs when deg(current) + deg(next) <= this (registers)
@@ -144,6 +150,7 @@ template <class C> struct Th {  // per-thread constants
     const float *llr;           // this thread's codeblock LLR row, already offset by r
     uint32_t r4;                // r * 4
     uint32_t r4m2;              // r * 4 + mag2_dist
+    char *p4, *p4m2;            // smem + r4, smem + r4m2
     int r, tile;
     int w4[C::tiles + 1];       // warp-uniform wrap offsets in bytes of a 4-byte-stride array: w4[t] = tile >= t ? -4 Zc : 0
 };
@@ -334,7 +341,11 @@ __device__ __forceinline__ void vn_entry_s(float &acc, const Th<C> &th)
     const uint32_t bits = load_bits<C, i>(th.smem + (C::bits_base(i) + 4 * back) + th.r4 + th.w4[t]);
     const bool isidx = ((bits ^ ((uint32_t)k << C::idx_shift(i))) & C::idx_mask(i)) == 0;
     // only the magnitude this edge uses is read (one 128-byte wavefront): mag2 on the argmin edge, mag1 elsewhere
+#if NRLDPC_VN_PSEL
+    const float mag = *reinterpret_cast<const float *>((isidx ? th.p4m2 : th.p4) + ((C::mags_base(i) + 4 * back) + th.w4[t]));
+#else
     const float mag = *reinterpret_cast<const float *>(th.smem + (C::mags_base(i) + 4 * back) + (isidx ? th.r4m2 : th.r4) + th.w4[t]);
+#endif
     acc = __fadd_rn(acc, __uint_as_float(__float_as_uint(mag) ^ ((bits << (31 - (DEGI - 1 - k))) & 0x80000000u)));
 }
 
@@ -473,13 +484,24 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     constexpr int NT = C::nwarps * 32, ZC = C::ZC;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __reduce_min_sync(0xffffffffu, tid >> 5);  // warp-uniform (REDUX writes a uniform register)
+#if NRLDPC_SUB_INTERLEAVE
+    // warp -> (tile, group) with the group in the low bits: the warps of one scheduler (warp % 4) then all
+    // run the same instruction stream (S = 2: even schedulers group 0, odd schedulers group 1)
+    const int sub = warp % C::S;
+    Th<C> th;
+    th.smem = smem;
+    th.tile = warp / C::S;
+#else
     const int sub = warp / C::tiles;
     Th<C> th;
     th.smem = smem;
     th.tile = warp % C::tiles;
+#endif
     th.r = th.tile * 32 + lane;
     th.r4 = (uint32_t)th.r * 4u;
     th.r4m2 = th.r4 + (uint32_t)C::mag2_dist;
+    th.p4 = smem + th.r4;
+    th.p4m2 = smem + th.r4m2;
 #pragma unroll
     for (int t = 0; t <= C::tiles; ++t) th.w4[t] = (th.tile >= t) ? -4 * ZC : 0;
 
