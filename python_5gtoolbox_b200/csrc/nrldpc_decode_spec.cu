@@ -28,6 +28,9 @@ namespace nrldpc {
 namespace {
 
 constexpr int kMaxS = 16;  // warp groups per r-tile
+#ifndef NRLDPC_COLD_FMA
+#define NRLDPC_COLD_FMA 1
+#endif
 #ifndef NRLDPC_VN_PSEL
 #define NRLDPC_VN_PSEL 1
 #endif
@@ -35,7 +38,7 @@ constexpr int kMaxS = 16;  // warp groups per r-tile
 #define NRLDPC_SUB_INTERLEAVE 0
 #endif
 #ifndef NRLDPC_SIGN_FMA
-#define NRLDPC_SIGN_FMA 1
+#define NRLDPC_SIGN_FMA 0
 #endif
 #ifndef NRLDPC_PF_SUM
 #define NRLDPC_PF_SUM 16  // prefetch the next check row's inputs when deg(current) + deg(next) <= this (registers)
@@ -259,36 +262,48 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
     cn_edges_s<C, I, ET>(q, m1, m2, synd, th, in, idxf, llr_e, std::make_integer_sequence<int, DEG>{});
     // signs of Lq and the argmin: an edge is "hot" when |Lq| == min1, i.e. min1 - |Lq| is +0 (never NaN
     // for finite inputs).  Edges that tie at min1 make min2 == min1, so any hot edge may carry the index.
+    constexpr uint32_t ALL = (1u << DEG) - 1u;
 #if NRLDPC_SIGN_FMA
     // Sign word on the FMA pipe (the check pass is bound by the ALU pipe): [Lq < 0] = sat(Lq * -inf)
     // exactly -- -inf/+inf saturate to 0/1 and 0 * inf = NaN saturates to +0 -- accumulated as an exact
     // small integer on top of 2^23, whose mantissa then holds the word.
-    uint32_t cold = 0;
     float saccf = 8388608.0f;
 #pragma unroll
     for (int k = 0; k < DEG; ++k) {
         const float neg = __saturatef(__fmul_rn(q[k], __uint_as_float(0xff800000u)));
-        saccf = __fmaf_rn(neg, (float)(1u << (DEG - 1 - k)), saccf);                      // sign of Lq on edge k -> bit DEG-1-k
-        cold = push_top_bit(cold, __float_as_uint(__fsub_rn(fabsf(m1), fabsf(q[k]))));  // 1 when |Lq| > min1
+        saccf = __fmaf_rn(neg, (float)(1u << (DEG - 1 - k)), saccf);  // sign of Lq on edge k -> bit DEG-1-k
     }
     const uint32_t sacc = __float_as_uint(saccf);
 #else
-    uint32_t sacc = 0, cold = 0;
+    uint32_t sacc = 0;
 #pragma unroll
-    for (int k = 0; k < DEG; ++k) {
-        sacc = push_top_bit(sacc, __float_as_uint(q[k]));                               // sign of Lq on edge k -> bit DEG-1-k
-        cold = push_top_bit(cold, __float_as_uint(__fsub_rn(fabsf(m1), fabsf(q[k]))));  // 1 when |Lq| > min1
-    }
+    for (int k = 0; k < DEG; ++k) sacc = push_top_bit(sacc, __float_as_uint(q[k]));  // sign of Lq on edge k -> bit DEG-1-k
 #endif
-    constexpr uint32_t ALL = (1u << DEG) - 1u;
+    // The argmin: an edge is "hot" when |Lq| == min1, i.e. min1 - |Lq| is +0 (never NaN for finite inputs),
+    // "cold" when it is negative.  Edges that tie at min1 make min2 == min1, so then ANY index gives the
+    // same messages.
+#if NRLDPC_COLD_FMA
+    // sum of the cold edges' positions, same exact-integer trick: kmin = sum(all k) - sum(cold k)
+    float coldf = 8388608.0f;
+#pragma unroll
+    for (int k = 1; k < DEG; ++k) {
+        const float c = __saturatef(__fmul_rn(__fsub_rn(fabsf(m1), fabsf(q[k])), __uint_as_float(0xff800000u)));
+        coldf = __fmaf_rn(c, (float)k, coldf);
+    }
+    const uint32_t kmin = (uint32_t)(DEG * (DEG - 1) / 2) - (__float_as_uint(coldf) & 0xffu);
+#else
+    uint32_t cold = 0;
+#pragma unroll
+    for (int k = 0; k < DEG; ++k) cold = push_top_bit(cold, __float_as_uint(__fsub_rn(fabsf(m1), fabsf(q[k]))));
     const uint32_t hot = ~cold & ALL;
     const uint32_t kmin = (uint32_t)(DEG - 32) + (uint32_t)__clz(hot);  // DEG-1 - (31 - clz): smallest hot k
+#endif
     // :199-202  Lr = alpha * sign_prod * sign(Lq) * max(minv - beta, 0), minv = min2 on the argmin edge
     // (beta == 0: max(m - 0, 0) == m for m >= +0)
     const float mag1 = B0 ? __fmul_rn(a.alpha, fabsf(m1)) : __fmul_rn(a.alpha, fmaxf(__fsub_rn(fabsf(m1), a.beta), 0.f));
     const float mag2 = B0 ? __fmul_rn(a.alpha, m2) : __fmul_rn(a.alpha, fmaxf(__fsub_rn(m2, a.beta), 0.f));
     const uint32_t sp = (uint32_t)((int)__float_as_uint(m1) >> 31);  // all ones when the sign product is -
-    const uint32_t nb = ((sacc ^ sp) & ALL) | (kmin << C::idx_shift(I));
+    const uint32_t nb = ((sacc ^ sp) & ALL) | ((kmin << C::idx_shift(I)) & C::idx_mask(I));
     *reinterpret_cast<float *>(rec) = mag1;
     *reinterpret_cast<float *>(rec + C::mag2_dist) = mag2;
     store_bits<C, I>(bp, nb);
