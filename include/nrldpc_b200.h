@@ -152,6 +152,39 @@ int nrldpc_crc_check(const int8_t *d_in, int B, int A, int poly_id, uint8_t *d_e
 int nrldpc_crc_encode_host(const int8_t *in, int B, int A, int poly_id, int8_t *out);
 int nrldpc_crc_check_host(const int8_t *in, int B, int A, int poly_id, uint8_t *err);
 
+/* ------------------------------------------------------------------ rate matching / recovery (callers' side) */
+/*
+ * nr_ldpc_ratematch.ratematch_ldpc(dn, Ncb, E, k0, Qm) for the B codeblocks of a transport block
+ * (py5gphy/ldpc/nr_ldpc_ratematch.py:64-97) followed by code block concatenation
+ * (py5gphy/nr_pdsch/nr_dlsch.py:66-68): bit selection from the circular buffer of length Ncb starting at k0,
+ * skipping the -1 fillers, repeating when E exceeds the buffer, then the Qm-row bit interleaver.
+ *   dn [B,N] int8 in {0,1,-1};  E [B] int32 output length of every codeblock (a multiple of Qm);
+ *   goff [B] int64 offset of codeblock b inside g (host variant: the running sum of E);  g int8.
+ */
+int nrldpc_ratematch(const int8_t *d_dn, int B, int N, int Ncb, int k0, int Qm, const int32_t *d_E,
+                     const long long *d_goff, int8_t *d_g, void *stream);
+int nrldpc_ratematch_host(const int8_t *dn, int B, int N, int Ncb, int k0, int Qm, const int32_t *E, int8_t *g);
+
+/*
+ * nr_ldpc_raterecover.raterecover_ldpc(LLr_fe, Ncb, N, k0, Qm, Zc, K_apo, K) for B codeblocks
+ * (py5gphy/ldpc/nr_ldpc_raterecover.py:6-65): de-interleave, put the E received LLRs back on the circular
+ * buffer (repeated positions are averaged: float64 sum in arrival order / count, :41-63), fillers
+ * [F0,F1) = [K_apo-2Zc, K-2Zc) get 10*max|LLr_fe| (:30,:64), everything else 0.
+ *   llr_g : the concatenated received LLRs, float32 (in_f64 = 0) or float64; arithmetic is float64.
+ *   out [B,N] float64 (out_f64 = 1, the reference's dtype) or float32 (what the fp32 decoder consumes).
+ */
+int nrldpc_raterecover(const void *d_llr_g, int in_f64, int B, int N, int Ncb, int k0, int Qm, int F0, int F1,
+                       const int32_t *d_E, const long long *d_goff, void *d_out, int out_f64, void *stream);
+int nrldpc_raterecover_host(const void *llr_g, int in_f64, int B, int N, int Ncb, int k0, int Qm, int Zc, int K_apo,
+                            int K, const int32_t *E, void *out, int out_f64);
+
+/*
+ * HARQ soft combining of DLSCHDecode / ULSCH_decoding (py5gphy/nr_pdsch/nr_dlsch_decode.py:80-87,
+ * py5gphy/nr_pusch/nr_ulsch_decode.py:81-88): out = a + c where either is 0, (a + c) / 2 elsewhere; float64.
+ */
+int nrldpc_harq_combine(const double *d_new, const double *d_cur, long long count, double *d_out, void *stream);
+int nrldpc_harq_combine_host(const double *nw, const double *cur, long long count, double *out);
+
 #ifdef __cplusplus
 }
 #endif

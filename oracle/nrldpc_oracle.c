@@ -294,6 +294,76 @@ int oracle_crc_encode(const int8_t *blk, int A, int poly_id, int8_t *out)
     return L;
 }
 
+/* ------------------------------------------------------------------ rate matching / recovery, HARQ combining */
+
+/*
+ * ratematch_ldpc(dn, Ncb, E, k0, Qm): py5gphy/ldpc/nr_ldpc_ratematch.py:64-97, statement for statement.
+ * dn[N] in {0,1,-1}, fe[E].
+ */
+int oracle_ratematch(const int8_t *dn, int N, int Ncb, int E, int k0, int Qm, int8_t *fe)
+{
+    if (N < Ncb || Qm <= 0 || E % Qm) return -1;
+    int8_t *ek = (int8_t *)malloc((size_t)(E > 0 ? E : 1));
+    int k = 0, j = 0;
+    while (k < E) { /* :82-87 bit selection, fillers skipped */
+        int8_t v = dn[(k0 + j) % Ncb];
+        if (v != -1) ek[k++] = v;
+        ++j;
+    }
+    /* :90-93 bit interleaving: d1 = ek.reshape(Qm, E/Qm); fe = d1.T.reshape(E) */
+    int cols = E / Qm;
+    for (int q = 0; q < Qm; ++q)
+        for (int e = 0; e < cols; ++e) fe[e * Qm + q] = ek[q * cols + e];
+    free(ek);
+    return 0;
+}
+
+/*
+ * raterecover_ldpc(LLr_fe, Ncb, N, k0, Qm, Zc, K_apo, K): py5gphy/ldpc/nr_ldpc_raterecover.py:6-65,
+ * statement for statement (float64).  out[N].
+ */
+int oracle_raterecover(const double *fe, int E, int Ncb, int N, int k0, int Qm, int Zc, int K_apo, int K, double *out)
+{
+    if (Qm <= 0 || E % Qm || E <= 0) return -1;
+    int cols = E / Qm;
+    double *ek = (double *)malloc(sizeof(double) * (size_t)E);
+    double mx = 0.0;
+    for (int e = 0; e < cols; ++e) /* :25-28 d1 = fe.reshape(E/Qm, Qm); ek = d1.T.reshape(E) */
+        for (int q = 0; q < Qm; ++q) ek[q * cols + e] = fe[e * Qm + q];
+    for (int e = 0; e < E; ++e) if (fabs(fe[e]) > mx) mx = fabs(fe[e]);
+    double max_llr = mx * 10; /* :30 */
+    int F0 = K_apo - 2 * Zc, F1 = K - 2 * Zc; /* :34 filler positions of dn */
+    int size = Ncb - (F1 - F0);               /* :38 */
+    int rep_num = (E + size - 1) / size;      /* :39 */
+    double *tmp = (double *)calloc((size_t)rep_num * Ncb, sizeof(double));
+    double *rep = (double *)malloc(sizeof(double) * (size_t)Ncb);
+    for (int p = 0; p < Ncb; ++p) rep[p] = 10000;
+    int rep_idx = -1, k = 0, j = 0;
+    while (k < E) { /* :47-62 */
+        int pos = (k0 + j) % Ncb;
+        if (pos == k0) ++rep_idx;
+        if (!(pos >= F0 && pos < F1)) tmp[(size_t)rep_idx * Ncb + pos] = ek[k++];
+        if (rep[pos] == 10000) rep[pos] = 1; else rep[pos] += 1;
+        ++j;
+    }
+    for (int p = 0; p < N; ++p) out[p] = 0.0;
+    for (int p = 0; p < Ncb; ++p) { /* :65 np.sum(tmp_buf, axis=0) / rep_buf: rows added in order */
+        double s = tmp[p];
+        for (int r = 1; r < rep_num; ++r) s += tmp[(size_t)r * Ncb + p];
+        out[p] = s / rep[p];
+    }
+    for (int p = F0; p < F1; ++p) if (p >= 0 && p < N) out[p] = max_llr; /* :66 */
+    free(ek); free(tmp); free(rep);
+    return 0;
+}
+
+/* HARQ combining loop of DLSCHDecode: py5gphy/nr_pdsch/nr_dlsch_decode.py:80-87 */
+void oracle_harq_combine(const double *nw, const double *cur, long n, double *out)
+{
+    for (long m = 0; m < n; ++m)
+        out[m] = (nw[m] == 0 || cur[m] == 0) ? nw[m] + cur[m] : (nw[m] + cur[m]) / 2;
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -157,5 +157,31 @@ def nr_crc_encode(blk, poly):
     return out[: blk.size + L].copy()
 
 
+def ratematch_ldpc(dn, Ncb, E, k0, Qm):
+    """py5gphy/ldpc/nr_ldpc_ratematch.py:64-97"""
+    dn = np.ascontiguousarray(dn, np.int8)
+    fe = np.empty(E, np.int8)
+    assert lib().oracle_ratematch(_p(dn, ctypes.c_int8), dn.size, int(Ncb), int(E), int(k0), int(Qm), _p(fe, ctypes.c_int8)) == 0
+    return fe
+
+
+def raterecover_ldpc(LLr_fe, Ncb, N, k0, Qm, Zc, K_apo, K):
+    """py5gphy/ldpc/nr_ldpc_raterecover.py:6-65 (float64)"""
+    fe = np.ascontiguousarray(LLr_fe, np.float64)
+    out = np.empty(N, np.float64)
+    assert lib().oracle_raterecover(_p(fe, ctypes.c_double), fe.size, int(Ncb), int(N), int(k0), int(Qm), int(Zc),
+                                    int(K_apo), int(K), _p(out, ctypes.c_double)) == 0
+    return out
+
+
+def harq_combine(new, cur):
+    """py5gphy/nr_pdsch/nr_dlsch_decode.py:80-87"""
+    a = np.ascontiguousarray(new, np.float64)
+    c = np.ascontiguousarray(cur, np.float64)
+    out = np.empty_like(a)
+    lib().oracle_harq_combine(_p(a, ctypes.c_double), _p(c, ctypes.c_double), ctypes.c_long(a.size), _p(out, ctypes.c_double))
+    return out
+
+
 def num_threads():
     return int(lib().oracle_num_threads())

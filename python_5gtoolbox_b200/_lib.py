@@ -57,6 +57,12 @@ def _declare(L):
         "nrldpc_crc_check": (i, [p, i, i, i, p, p]),
         "nrldpc_crc_encode_host": (i, [p, i, i, i, p]),
         "nrldpc_crc_check_host": (i, [p, i, i, i, p]),
+        "nrldpc_ratematch": (i, [p, i, i, i, i, i, p, p, p, p]),
+        "nrldpc_ratematch_host": (i, [p, i, i, i, i, i, p, p]),
+        "nrldpc_raterecover": (i, [p, i, i, i, i, i, i, i, i, p, p, p, i, p]),
+        "nrldpc_raterecover_host": (i, [p, i, i, i, i, i, i, i, i, i, p, p, i]),
+        "nrldpc_harq_combine": (i, [p, p, ll, p, p]),
+        "nrldpc_harq_combine_host": (i, [p, p, ll, p]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError here = the .so does not export what the header declares

@@ -214,3 +214,111 @@ def count_errors(ref, got, K, iters=None, counters=None):
                                                   iters.data_ptr() if iters is not None else None,
                                                   counters.data_ptr(), _stream_ptr()), "count_errors")
     return counters
+
+
+# ------------------------------------------------------------------ rate matching / recovery, HARQ, CRC (callers' side)
+
+def _offsets(E_list):
+    E = np.ascontiguousarray(E_list, np.int32).reshape(-1)
+    off = np.zeros(E.size, np.int64)
+    if E.size > 1:
+        off[1:] = np.cumsum(E[:-1], dtype=np.int64)
+    return E, off, int(E.sum(dtype=np.int64))
+
+
+def ratematch_batch(dn, Ncb, E_list, k0, Qm):
+    """ratematch_ldpc for the B codeblocks of a transport block + code block concatenation
+    (py5gphy/ldpc/nr_ldpc_ratematch.py:64-97, py5gphy/nr_pdsch/nr_dlsch.py:66-68).
+    dn int8 [B,N] (NumPy or CUDA tensor), E_list the B output lengths -> g int8 [sum(E)] of the same kind."""
+    assert dn.ndim == 2
+    B, N = dn.shape
+    E, off, total = _offsets(E_list)
+    assert E.size == B and N >= Ncb and Qm in [1, 2, 4, 6, 8] and not np.any(E % Qm)
+    L = _lib.lib()
+    if _is_torch(dn):
+        import torch
+        assert dn.is_cuda and dn.dtype == torch.int8 and dn.is_contiguous()
+        g = torch.empty((total,), dtype=torch.int8, device=dn.device)
+        dE, doff = torch.from_numpy(E).to(dn.device), torch.from_numpy(off).to(dn.device)
+        with torch.cuda.device(dn.device):
+            _lib.check(L.nrldpc_ratematch(dn.data_ptr(), B, N, int(Ncb), int(k0), int(Qm), dE.data_ptr(), doff.data_ptr(),
+                                          g.data_ptr(), _stream_ptr()), "ratematch")
+        return g
+    dn = np.ascontiguousarray(dn, np.int8)
+    g = np.empty(total, np.int8)
+    _lib.check(L.nrldpc_ratematch_host(dn.ctypes.data, B, N, int(Ncb), int(k0), int(Qm), E.ctypes.data, g.ctypes.data), "ratematch")
+    return g
+
+
+def raterecover_batch(llr_g, E_list, Ncb, N, k0, Qm, Zc, K_apo, K, out_f64=True):
+    """raterecover_ldpc for B codeblocks (py5gphy/ldpc/nr_ldpc_raterecover.py:6-65): llr_g = the
+    concatenated received LLRs (float32 or float64; NumPy or CUDA tensor) -> [B,N] float64 (the
+    reference's dtype) or float32 (out_f64=False: what the fp32 decoder consumes)."""
+    E, off, total = _offsets(E_list)
+    B = E.size
+    assert llr_g.ndim == 1 and llr_g.shape[0] == total and not np.any(E % Qm) and np.all(E > 0)
+    L = _lib.lib()
+    if _is_torch(llr_g):
+        import torch
+        assert llr_g.is_cuda and llr_g.is_contiguous() and llr_g.dtype in (torch.float32, torch.float64)
+        out = torch.empty((B, N), dtype=torch.float64 if out_f64 else torch.float32, device=llr_g.device)
+        dE, doff = torch.from_numpy(E).to(llr_g.device), torch.from_numpy(off).to(llr_g.device)
+        with torch.cuda.device(llr_g.device):
+            _lib.check(L.nrldpc_raterecover(llr_g.data_ptr(), int(llr_g.dtype == torch.float64), B, int(N), int(Ncb), int(k0),
+                                            int(Qm), int(K_apo - 2 * Zc), int(K - 2 * Zc), dE.data_ptr(), doff.data_ptr(),
+                                            out.data_ptr(), int(out_f64), _stream_ptr()), "raterecover")
+        return out
+    in64 = np.asarray(llr_g).dtype != np.float32
+    x = np.ascontiguousarray(llr_g, np.float64 if in64 else np.float32)
+    out = np.empty((B, N), np.float64 if out_f64 else np.float32)
+    _lib.check(L.nrldpc_raterecover_host(x.ctypes.data, int(in64), B, int(N), int(Ncb), int(k0), int(Qm), int(Zc), int(K_apo),
+                                         int(K), E.ctypes.data, out.ctypes.data, int(out_f64)), "raterecover")
+    return out
+
+
+def harq_combine(new, cur):
+    """HARQ soft combining of DLSCHDecode / ULSCH_decoding (py5gphy/nr_pdsch/nr_dlsch_decode.py:80-87), float64."""
+    L = _lib.lib()
+    if _is_torch(new):
+        import torch
+        assert new.is_cuda and cur.is_cuda and new.dtype == torch.float64 and cur.dtype == torch.float64
+        assert new.is_contiguous() and cur.is_contiguous() and new.shape == cur.shape
+        out = torch.empty_like(new)
+        with torch.cuda.device(new.device):
+            _lib.check(L.nrldpc_harq_combine(new.data_ptr(), cur.data_ptr(), new.numel(), out.data_ptr(), _stream_ptr()), "harq_combine")
+        return out
+    a = np.ascontiguousarray(new, np.float64)
+    c = np.ascontiguousarray(cur, np.float64)
+    assert a.shape == c.shape
+    out = np.empty_like(a)
+    _lib.check(L.nrldpc_harq_combine_host(a.ctypes.data, c.ctypes.data, a.size, out.ctypes.data), "harq_combine")
+    return out
+
+
+_POLY_ID = {"6": 0, "11": 1, "16": 2, "24A": 3, "24B": 4, "24C": 5}
+_POLY_LEN = {"6": 6, "11": 11, "16": 16, "24A": 24, "24B": 24, "24C": 24}
+
+
+def crc_encode_device(blk, poly):
+    """nr_crc_encode for B blocks on CUDA tensors: int8 [B,A] -> int8 [B,A+L] (py5gphy/crc/crc.py:4-41)."""
+    import torch
+    key = str(poly).upper()
+    assert key in _POLY_ID and blk.is_cuda and blk.dtype == torch.int8 and blk.is_contiguous() and blk.ndim == 2
+    B, A = blk.shape
+    out = torch.empty((B, A + _POLY_LEN[key]), dtype=torch.int8, device=blk.device)
+    with torch.cuda.device(blk.device):
+        _lib.check(_lib.lib().nrldpc_crc_encode(blk.data_ptr(), B, A, _POLY_ID[key], out.data_ptr(), _stream_ptr()), "crc_encode")
+    return out
+
+
+def crc_check_device(blkandcrc, poly):
+    """nr_crc_decode's error flag for B blocks on CUDA tensors: int8 [B,A+L] -> uint8 [B] (py5gphy/crc/crc.py:43-88)."""
+    import torch
+    key = str(poly).upper()
+    assert key in _POLY_ID and blkandcrc.is_cuda and blkandcrc.dtype == torch.int8 and blkandcrc.is_contiguous()
+    B, n = blkandcrc.shape
+    err = torch.empty((B,), dtype=torch.uint8, device=blkandcrc.device)
+    with torch.cuda.device(blkandcrc.device):
+        _lib.check(_lib.lib().nrldpc_crc_check(blkandcrc.data_ptr(), B, n - _POLY_LEN[key], _POLY_ID[key], err.data_ptr(),
+                                               _stream_ptr()), "crc_check")
+    return err

@@ -1,0 +1,13 @@
+"""Mirror of py5gphy/nr_pdsch/nr_dlsch_decode.py: DLSCHDecode, batched over the codeblocks."""
+import numpy as np
+
+from .. import sch
+
+
+def DLSCHDecode(LLr, TBSize, Qm, coderateby1024, num_of_layers, rv, TBS_LBRM, LDPC_decoder_config, HARQ_on=False,
+                current_LLr_dns=np.array([])):
+    """(status, tbblk, new_LLr_dns) = DLSCHDecode(...) -- py5gphy/nr_pdsch/nr_dlsch_decode.py:13-109:
+    de-rate matching, optional HARQ combining with current_LLr_dns, LDPC decoding with
+    LDPC_decoder_config = {"L", "algo", "alpha", "beta"}, CB CRC (ignored) and TB CRC (= status)."""
+    return sch.sch_decode(LLr, np.asarray(LLr).size, TBSize, Qm, coderateby1024, num_of_layers, rv, sch.lbrm_ncb(TBS_LBRM),
+                          LDPC_decoder_config, HARQ_on, current_LLr_dns)

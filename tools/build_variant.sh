@@ -10,4 +10,4 @@ nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler
   --expt-relaxed-constexpr "$@" -c nrldpc_decode_spec.cu -o ../../build/variants/spec_$name.o 2> ../../build/variants/spec_$name.log
 grep -E "registers|spill" ../../build/variants/spec_$name.log | sed -n 3,4p | tr '\n' ' '; echo
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../../build/variants/libnrldpc_$name.so nrldpc_api.o nrldpc_tables.o \
-  nrldpc_encode.o nrldpc_decode_qc.o ../../build/variants/spec_$name.o nrldpc_generic.o nrldpc_util.o -lcudart
+  nrldpc_encode.o nrldpc_decode_qc.o ../../build/variants/spec_$name.o nrldpc_generic.o nrldpc_util.o nrldpc_ratematch.o -lcudart
