@@ -283,14 +283,15 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
     // "cold" when it is negative.  Edges that tie at min1 make min2 == min1, so then ANY index gives the
     // same messages.
 #if NRLDPC_COLD_FMA
-    // sum of the cold edges' positions, same exact-integer trick: kmin = sum(all k) - sum(cold k)
-    float coldf = 8388608.0f;
+    // position of the hot edge = sum(all k) - sum(cold k), with cold = sat(d * -inf) in {0, 1} exactly and the
+    // sum kept as an exact small integer on top of 2^23, whose low mantissa bits are then the position
+    float hotpos = 8388608.0f + (float)(DEG * (DEG - 1) / 2);
 #pragma unroll
     for (int k = 1; k < DEG; ++k) {
         const float c = __saturatef(__fmul_rn(__fsub_rn(fabsf(m1), fabsf(q[k])), __uint_as_float(0xff800000u)));
-        coldf = __fmaf_rn(c, (float)k, coldf);
+        hotpos = __fmaf_rn(c, -(float)k, hotpos);
     }
-    const uint32_t kmin = (uint32_t)(DEG * (DEG - 1) / 2) - (__float_as_uint(coldf) & 0xffu);
+    const uint32_t kmin = __float_as_uint(hotpos);  // low bits; masked to the index field below
 #else
     uint32_t cold = 0;
 #pragma unroll
@@ -316,10 +317,14 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
 }
 
 // Channel LLR of the degree-1 extension variable of row-block I (0 for the core rows), -0.0 -> +0.0.
-template <class C, int I> __device__ __forceinline__ float load_ext_llr(const Th<C> &th)
+// (-0.0 -> +0.0 only when the syndrome reads the sign bit of LLR + Lr (ET); the messages do not depend on
+// the sign of a zero LLR: x = LLR + Lr and Lq = x - Lr give the same values either way.)
+template <class C, int I, bool ET> __device__ __forceinline__ float load_ext_llr(const Th<C> &th)
 {
-    if constexpr (I >= 4) return __fadd_rn(__ldg(th.llr + (C::kb + I - 2) * C::ZC), 0.0f);
-    else return 0.f;
+    if constexpr (I >= 4) {
+        const float v = __ldg(th.llr + (C::kb + I - 2) * C::ZC);
+        return ET ? __fadd_rn(v, 0.0f) : v;
+    } else return 0.f;
 }
 
 // The rows of warp group SUB, software-pipelined: the compiler cannot move a row's shared-memory loads
@@ -333,7 +338,7 @@ __device__ __forceinline__ void cn_pass_s(const DecArgs &a, const Th<C> &th, int
     constexpr int I = kRows<C>.item[SUB][O];
     if constexpr (O + 1 < kRows<C>.n[SUB]) {
         constexpr int In = kRows<C>.item[SUB][O + 1];
-        const float llr_nxt = load_ext_llr<C, In>(th);
+        const float llr_nxt = load_ext_llr<C, In, ET>(th);
         if constexpr (C::deg(I) + C::deg(In) <= NRLDPC_PF_SUM) {
             const RowIn<C, In> in_nxt = load_row<C, In>(th);
             cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
@@ -389,9 +394,10 @@ __device__ __forceinline__ void vn_store_s(const Th<C> &th, const float lq)
 }
 
 // Channel LLR of core column-block J; the 2Zc punctured systematic bits start at LLR 0 (:43).
+// (no -0.0 -> +0.0 here: the sum of the messages is never -0.0, so LLR + sum has the same value and sign.)
 template <class C, int J> __device__ __forceinline__ float load_col_llr(const Th<C> &th)
 {
-    if constexpr (J >= 2) return __fadd_rn(__ldg(th.llr + (J - 2) * C::ZC), 0.0f);
+    if constexpr (J >= 2) return __ldg(th.llr + (J - 2) * C::ZC);
     else return 0.f;
 }
 
@@ -453,7 +459,7 @@ template <class C, bool ET, bool B0, int SUB = 0>
 __device__ __forceinline__ void run_cn(int sub, const DecArgs &a, const Th<C> &th, int *flag)
 {
     if constexpr (SUB < C::S) {
-        if (sub == SUB) cn_pass_s<C, ET, B0, SUB>(a, th, flag, load_row<C, kRows<C>.item[SUB][0]>(th), load_ext_llr<C, kRows<C>.item[SUB][0]>(th));
+        if (sub == SUB) cn_pass_s<C, ET, B0, SUB>(a, th, flag, load_row<C, kRows<C>.item[SUB][0]>(th), load_ext_llr<C, kRows<C>.item[SUB][0], ET>(th));
         else run_cn<C, ET, B0, SUB + 1>(sub, a, th, flag);
     }
 }
