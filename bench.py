@@ -80,6 +80,7 @@ def cpu_reference_run(steps, warmup, sample_cbs=None, early_term=0):
     import numpy as np
     from oracle import oracle as O
     O.build()
+    O.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     threads = O.num_threads()
     n = sample_cbs or max(threads * 100, 64)   # ~26 ms per codeblock per core -> a few seconds per step
     rng = np.random.default_rng(0x5601)
@@ -234,8 +235,9 @@ def run_ours(args):
                                  "wavefronts; see DESIGN.md and profiles/"},
             "clocks": clk.summary(),
         }
-        if not args.no_cpu:
-            gbps, threads, n, sps = cpu_reference_run(1, 0, sample_cbs=max(400 * (os.cpu_count() or 1), 256))  # ~10 s of CPU work
+        if not args.no_cpu and world == 1:   # reported at N=1 only (rank 0); ~10 s of CPU work on all host cores
+            ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            gbps, threads, n, sps = cpu_reference_run(1, 0, sample_cbs=max(400 * ncores, 256))
             out["cpu_baseline"] = {"value": gbps, "unit": "Gbit/s", "cores": threads, "kind": "port",
                                    "sample": f"{n} codeblocks of the same workload, float64 C port of the reference (oracle/), "
                                              f"{threads} OpenMP threads, {sps:.2f} s"}

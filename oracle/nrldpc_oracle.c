@@ -364,6 +364,16 @@ void oracle_harq_combine(const double *nw, const double *cur, long n, double *ou
         out[m] = (nw[m] == 0 || cur[m] == 0) ? nw[m] + cur[m] : (nw[m] + cur[m]) / 2;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1: the CPU-baseline legs of bench.py ask for every host core explicitly */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -185,3 +185,8 @@ def harq_combine(new, cur):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n):
+    """Override OMP_NUM_THREADS (torchrun sets it to 1) for the CPU-baseline legs of bench.py."""
+    lib().oracle_set_num_threads(int(n))

@@ -233,8 +233,17 @@ __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, floa
     }
     if constexpr (ET) synd ^= __float_as_uint(x);  // sign bit = hard decision LQ<0 (:107-108)
     q[K] = __fsub_rn(x, lr);                        // Lq = LQ - Lr (:131)
-    m2 = fminf(m2, fmaxf(fabsf(m1), fabsf(q[K])));
-    m1 = min_xorsign_abs(m1, q[K]);                 // |m1| = first minimum, sign = running sign product
+    // |m1| = first minimum, sign of m1 = running sign product, m2 = second minimum (the first two edges
+    // spelled out: no arithmetic against the +inf start values)
+    if constexpr (K == 0) {
+        m1 = q[0];
+    } else if constexpr (K == 1) {
+        m2 = fmaxf(fabsf(m1), fabsf(q[1]));
+        m1 = min_xorsign_abs(m1, q[1]);
+    } else {
+        m2 = fminf(m2, fmaxf(fabsf(m1), fabsf(q[K])));
+        m1 = min_xorsign_abs(m1, q[K]);
+    }
 }
 
 template <class C, int I, bool ET, int... K>
