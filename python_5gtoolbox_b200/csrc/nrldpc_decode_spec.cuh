@@ -1,0 +1,656 @@
+// nrldpc_decode_spec.cuh -- flooding min-sum decoder kernels with (bgn, Zc) known at compile time.
+// (template code; one translation unit per instantiated (bgn, Zc): nrldpc_decode_spec_bgX_ZZZ.cu)
+//
+// Same algorithm, schedule and fp32 operation order as nrldpc_decode_qc.cu (the table-driven kernel):
+// py5gphy/ldpc/nr_ldpc_decode.py:51-143 (decode_ldpc) and :178-227 (_min_sum_process).  The whole base
+// graph is unrolled at compile time from the constexpr TS 38.212 tables, so every shift, column offset,
+// record offset and sign-bit position is an immediate and each warp group runs straight-line code.
+//
+// The kernel is bound by the SM's ALU pipe (LOP3/SHF/FMNMX/ISETP/SEL issue at half rate), not by HBM or
+// shared memory, so the design removes ALU instructions from the per-edge path:
+//   * circulant shifts cost no instruction: every shared-memory array that is read through a rotation
+//     (posteriors LQ in the check pass, row records in the variable pass) carries 32 extra elements that
+//     mirror its first 32, and the (r + P) mod Zc wrap becomes a WARP-UNIFORM choice between offset 0
+//     and -Zc (tile >= ceil((Zc-P)/32)), held in uniform registers: LDS [R + UR + imm];
+//   * the argmin of a check row is found after the two minima are known, from the sign of
+//     (min1 - |Lq|) computed on the FMA pipe, instead of a compare + select per edge;
+//   * sign/argmin words are 8-bit for rows of degree <= 5, 16-bit up to degree 12 and 32-bit above,
+//     interleaved so that all of them have a 4-byte stride (one set of wrap offsets, no bank conflicts).
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <utility>
+
+#include "nrldpc_decode.cuh"
+#define NRLDPC_TABLE static constexpr
+#include "../../include/nrldpc_bg_tables.inc"
+
+namespace nrldpc {
+
+namespace {
+
+constexpr int kMaxS = 16;  // warp groups per r-tile
+#ifndef NRLDPC_COLD_FMA
+#define NRLDPC_COLD_FMA 1
+#endif
+#ifndef NRLDPC_VN_PSEL
+#define NRLDPC_VN_PSEL 1
+#endif
+#ifndef NRLDPC_SUB_INTERLEAVE
+#define NRLDPC_SUB_INTERLEAVE 0
+#endif
+#ifndef NRLDPC_SIGN_FMA
+#define NRLDPC_SIGN_FMA 0
+#endif
+#ifndef NRLDPC_PF_SUM
+#define NRLDPC_PF_SUM 16  // prefetch the next check row's inputs when deg(current) + deg(next) <= this (registers)
+#endif
+
+template <int BGN> struct Graph;
+template <> struct Graph<1> {
+    static constexpr int rows = NRLDPC_BG1_ROWS, cols = NRLDPC_BG1_COLS, nnz = NRLDPC_BG1_NNZ, kb = 22;
+    static constexpr int rowptr(int i) { return nrldpc_bg1_rowptr[i]; }
+    static constexpr int col(int e) { return nrldpc_bg1_col[e]; }
+    static constexpr int shift(int s, int e) { return nrldpc_bg1_shift[s][e]; }
+};
+template <> struct Graph<2> {
+    static constexpr int rows = NRLDPC_BG2_ROWS, cols = NRLDPC_BG2_COLS, nnz = NRLDPC_BG2_NNZ, kb = 10;
+    static constexpr int rowptr(int i) { return nrldpc_bg2_rowptr[i]; }
+    static constexpr int col(int e) { return nrldpc_bg2_col[e]; }
+    static constexpr int shift(int s, int e) { return nrldpc_bg2_shift[s][e]; }
+};
+
+constexpr int ils_of(int Zc)
+{
+    constexpr int a[8] = {2, 3, 5, 7, 9, 11, 13, 15};
+    for (int s = 0; s < 8; ++s)
+        for (int z = a[s]; z <= 384; z *= 2)
+            if (z == Zc) return s;
+    return -1;
+}
+
+template <int BGN, int ZC_> struct Code {
+    using G = Graph<BGN>;
+    static constexpr int bgn = BGN, ZC = ZC_, iLS = ils_of(ZC_);
+    static_assert(iLS >= 0 && ZC_ % 32 == 0, "specialised kernels need a lifting size that is a multiple of 32");
+    static constexpr int nrows = G::rows, kb = G::kb, ncore = G::kb + 4, nnz = G::nnz;
+    static constexpr int K = kb * ZC, N = (G::cols - 2) * ZC, Nfull = G::cols * ZC;
+    static constexpr int tiles = ZC / 32, S = (32 / tiles) < kMaxS ? (32 / tiles) : kMaxS, nwarps = tiles * S;
+    static constexpr int LQS = ZC + 32;  // elements per rotated array: Zc + the 32 mirrored ones
+    static constexpr int deg(int i) { return G::rowptr(i + 1) - G::rowptr(i); }
+    static constexpr int P(int e) { return G::shift(iLS, e) % ZC; }
+    static constexpr int row_of(int e) { int i = 0; while (G::rowptr(i + 1) <= e) ++i; return i; }
+    // column view, ascending row-block = the reference's summation order (:126)
+    static constexpr int cdeg(int j) { int n = 0; for (int e = 0; e < nnz; ++e) n += (G::col(e) == j); return n; }
+    static constexpr int cedge(int j, int n)
+    {
+        for (int e = 0; e < nnz; ++e)
+            if (G::col(e) == j && n-- == 0) return e;
+        return -1;
+    }
+    // Tile index from which the rotation by `shift` wraps for the whole warp: lanes of tile T read
+    // index r + shift - (T >= wrap_tile ? Zc : 0), which stays inside [0, Zc + 32).
+    static constexpr int wrap_tile(int shift) { return (ZC - shift + 31) / 32; }
+
+    // sign/argmin word of a row: kind 0 = 8 bit (deg <= 5: 5 signs + 3 index bits), 1 = 16 bit
+    // (deg <= 12: 12 + 4), 2 = 32 bit (deg <= 24: 24 + 5).  Bit deg-1-k = sign of Lr on edge k.
+    static constexpr int kind(int i) { return deg(i) > 12 ? 2 : (deg(i) > 5 ? 1 : 0); }
+    static constexpr int rank(int i) { int n = 0; for (int x = 0; x < i; ++x) n += (kind(x) == kind(i)); return n; }
+    static constexpr int count(int kd) { int n = 0; for (int x = 0; x < nrows; ++x) n += (kind(x) == kd); return n; }
+    static constexpr int idx_shift(int i) { return kind(i) == 2 ? 24 : (kind(i) == 1 ? 12 : 5); }
+    static constexpr uint32_t idx_mask(int i) { return kind(i) == 2 ? 0x1f000000u : (kind(i) == 1 ? 0xf000u : 0xe0u); }
+    // shared-memory layout (bytes)
+    static constexpr int off_lq = 0;                                          // float LQ[ncore][LQS]
+    static constexpr int off_mags = off_lq + ncore * LQS * 4;                 // float mag1[nrows][LQS], then mag2[nrows][LQS]
+    static constexpr int mag2_dist = nrows * LQS * 4;                         // bytes from a row's mag1 to its mag2 (multiple of 128: same banks)
+    static constexpr int off_b32 = off_mags + 2 * mag2_dist;                  // uint32 [count(2)][LQS]
+    static constexpr int off_b16 = off_b32 + count(2) * LQS * 4;              // uint16 pairs of rows interleaved
+    static constexpr int off_b8 = off_b16 + ((count(1) + 1) / 2) * LQS * 4;   // uint8 quads of rows interleaved
+    static constexpr int off_ext = off_b8 + ((count(0) + 3) / 4) * LQS * 4;   // packed hard bits of the extension columns
+    static constexpr int smem_bytes = (off_ext + (nrows - 4) * tiles * 4 + 15) & ~15;
+    static constexpr int lq_base(int j) { return off_lq + j * LQS * 4; }
+    static constexpr int mags_base(int i) { return off_mags + i * LQS * 4; }  // mag1 of check 0; mag2 sits mag2_dist further
+    static constexpr int bits_base(int i)  // the word of check r sits at bits_base(i) + 4 r
+    {
+        return kind(i) == 2 ? off_b32 + rank(i) * LQS * 4
+             : kind(i) == 1 ? off_b16 + (rank(i) / 2) * LQS * 4 + (rank(i) % 2) * 2
+                            : off_b8 + (rank(i) / 4) * LQS * 4 + (rank(i) % 4);
+    }
+};
+
+struct Deal { int n[kMaxS]; int item[kMaxS][64]; };
+
+// rows by degree (descending, stable), longest-processing-time-first onto the S warp groups with the
+// measured cost model of a row: 13 issue slots per edge + 25 per row
+template <class C> constexpr Deal deal_rows()
+{
+    Deal d{};
+    int order[64] = {}, load[kMaxS] = {};
+    for (int i = 0; i < C::nrows; ++i) order[i] = i;
+    for (int i = 1; i < C::nrows; ++i)  // insertion sort, stable
+        for (int p = i; p > 0 && C::deg(order[p - 1]) < C::deg(order[p]); --p) { int t = order[p]; order[p] = order[p - 1]; order[p - 1] = t; }
+    for (int p = 0; p < C::nrows; ++p) {
+        int best = 0;
+        for (int s = 1; s < C::S; ++s) if (load[s] < load[best]) best = s;
+        d.item[best][d.n[best]++] = order[p];
+        load[best] += 13 * C::deg(order[p]) + 25;
+    }
+    return d;
+}
+// core columns: longest-processing-time-first onto the S groups
+template <class C> constexpr Deal deal_cols()
+{
+    Deal d{};
+    int order[64] = {}, load[kMaxS] = {};
+    for (int j = 0; j < C::ncore; ++j) order[j] = j;
+    for (int i = 1; i < C::ncore; ++i)
+        for (int p = i; p > 0 && C::cdeg(order[p - 1]) < C::cdeg(order[p]); --p) { int t = order[p]; order[p] = order[p - 1]; order[p - 1] = t; }
+    for (int p = 0; p < C::ncore; ++p) {
+        int best = 0;
+        for (int s = 1; s < C::S; ++s) if (load[s] < load[best]) best = s;
+        d.item[best][d.n[best]++] = order[p];
+        load[best] += 7 * C::cdeg(order[p]) + 6;
+    }
+    return d;
+}
+template <class C> inline constexpr Deal kRows = deal_rows<C>();
+template <class C> inline constexpr Deal kCols = deal_cols<C>();
+
+template <class C> struct Th {  // per-thread constants
+    char *smem;                 // the CTA's codeblock state
+    const float *llr;           // this thread's codeblock LLR row, already offset by r
+    uint32_t r4;                // r * 4
+    uint32_t r4m2;              // r * 4 + mag2_dist
+    char *p4, *p4m2;            // smem + r4, smem + r4m2
+    int r, tile;
+    int w4[C::tiles + 1];       // warp-uniform wrap offsets in bytes of a 4-byte-stride array: w4[t] = tile >= t ? -4 Zc : 0
+};
+
+// sign/argmin word access
+template <class C, int I> __device__ __forceinline__ uint32_t load_bits(const char *p)
+{
+    if constexpr (C::kind(I) == 2) return *reinterpret_cast<const uint32_t *>(p);
+    else if constexpr (C::kind(I) == 1) return *reinterpret_cast<const uint16_t *>(p);
+    else return *reinterpret_cast<const uint8_t *>(p);
+}
+template <class C, int I> __device__ __forceinline__ void store_bits(char *p, uint32_t v)
+{
+    if constexpr (C::kind(I) == 2) *reinterpret_cast<uint32_t *>(p) = v;
+    else if constexpr (C::kind(I) == 1) *reinterpret_cast<uint16_t *>(p) = (uint16_t)v;
+    else *reinterpret_cast<uint8_t *>(p) = (uint8_t)v;
+}
+
+// acc = acc << 1 | (top bit of v)
+__device__ __forceinline__ uint32_t push_top_bit(uint32_t acc, uint32_t v) { return __funnelshift_l(v, acc, 1); }
+
+// Posterior LQ of the variable on edge e of a check row with lifted index r: LQ[col][(r + P) mod Zc].
+template <class C, int E> __device__ __forceinline__ float load_lq_rot(const Th<C> &th)
+{
+    constexpr int P = C::P(E), t = C::wrap_tile(P);
+    return *reinterpret_cast<const float *>(th.smem + (C::lq_base(C::G::col(E)) + 4 * P) + th.r4 + th.w4[t]);
+}
+
+// What a check row reads from shared memory: its record and the posteriors of its core variables.
+template <class C, int I> struct RowIn {
+    static constexpr int NC = (I >= 4) ? C::deg(I) - 1 : C::deg(I);
+    float2 m;
+    uint32_t bits;
+    float x[NC];
+};
+template <class C, int I, int... K>
+__device__ __forceinline__ void load_row_x(RowIn<C, I> &in, const Th<C> &th, std::integer_sequence<int, K...>)
+{
+    ((in.x[K] = load_lq_rot<C, C::G::rowptr(I) + K>(th)), ...);
+}
+// r4 (+ the uniform wrap offset) must not be folded into per-lane registers hoisted out of the iteration
+// loop: the sum is made opaque here so that the wrap offsets stay in uniform registers (LDS [R + UR + imm]).
+template <class C> __device__ __forceinline__ Th<C> opaque(Th<C> th)
+{
+    asm volatile("" : "+r"(th.r4), "+r"(th.r4m2));
+    return th;
+}
+
+template <class C, int I> __device__ __forceinline__ RowIn<C, I> load_row(const Th<C> &th_)
+{
+    const Th<C> th = opaque(th_);
+    RowIn<C, I> in;
+    in.m.x = *reinterpret_cast<const float *>(th.smem + C::mags_base(I) + th.r4);
+    in.m.y = *reinterpret_cast<const float *>(th.smem + (C::mags_base(I) + C::mag2_dist) + th.r4);
+    in.bits = load_bits<C, I>(th.smem + C::bits_base(I) + th.r4);
+    load_row_x<C, I>(in, th, std::make_integer_sequence<int, RowIn<C, I>::NC>{});
+    return in;
+}
+
+template <class C, int I, int K, bool ET>
+__device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, float &m2, uint32_t &synd, const Th<C> &th,
+                                          const RowIn<C, I> &in, uint32_t idxf, float llr_e)
+{
+    constexpr int DEG = C::deg(I);
+    constexpr bool EXT = I >= 4;
+    const bool isidx = idxf == ((uint32_t)K << C::idx_shift(I));
+    const float lr = record_lr(in.m, isidx, in.bits << (31 - (DEG - 1 - K)));
+    float x;
+    if constexpr (EXT && K == DEG - 1) {
+        x = __fadd_rn(llr_e, lr);  // posterior of the degree-1 extension variable (:126)
+        if constexpr (ET) {
+            const uint32_t hb = __ballot_sync(0xffffffffu, x < 0.f);
+            if ((th.r & 31) == 0) reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + th.tile] = hb;
+        }
+    } else {
+        x = in.x[K];
+    }
+    if constexpr (ET) synd ^= __float_as_uint(x);  // sign bit = hard decision LQ<0 (:107-108)
+    q[K] = __fsub_rn(x, lr);                        // Lq = LQ - Lr (:131)
+    // |m1| = first minimum, sign of m1 = running sign product, m2 = second minimum (the first two edges
+    // spelled out: no arithmetic against the +inf start values)
+    if constexpr (K == 0) {
+        m1 = q[0];
+    } else if constexpr (K == 1) {
+        m2 = fmaxf(fabsf(m1), fabsf(q[1]));
+        m1 = min_xorsign_abs(m1, q[1]);
+    } else {
+        m2 = fminf(m2, fmaxf(fabsf(m1), fabsf(q[K])));
+        m1 = min_xorsign_abs(m1, q[K]);
+    }
+}
+
+template <class C, int I, bool ET, int... K>
+__device__ __forceinline__ void cn_edges_s(float (&q)[C::deg(I)], float &m1, float &m2, uint32_t &synd, const Th<C> &th,
+                                           const RowIn<C, I> &in, uint32_t idxf, float llr_e,
+                                           std::integer_sequence<int, K...>)
+{
+    (cn_edge_s<C, I, K, ET>(q, m1, m2, synd, th, in, idxf, llr_e), ...);
+}
+
+// One check row of row-block I (compile time), lifted index r: syndrome bit of the current hard
+// decisions, then the min-sum update of its record from Lq = LQ - Lr_old
+// (py5gphy/ldpc/nr_ldpc_decode.py:107-123, :178-227).
+template <class C, int I, bool ET, bool B0>
+__device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int *flag, const RowIn<C, I> &in,
+                                         const float llr_e)
+{
+    constexpr int DEG = C::deg(I);
+    char *rec = th.smem + C::mags_base(I) + th.r4;
+    char *bp = th.smem + C::bits_base(I) + th.r4;
+    const uint32_t idxf = in.bits & C::idx_mask(I);
+    float q[DEG];
+    float m1 = __uint_as_float(kInfBits), m2 = m1;
+    uint32_t synd = 0;
+    cn_edges_s<C, I, ET>(q, m1, m2, synd, th, in, idxf, llr_e, std::make_integer_sequence<int, DEG>{});
+    // signs of Lq and the argmin: an edge is "hot" when |Lq| == min1, i.e. min1 - |Lq| is +0 (never NaN
+    // for finite inputs).  Edges that tie at min1 make min2 == min1, so any hot edge may carry the index.
+    constexpr uint32_t ALL = (1u << DEG) - 1u;
+#if NRLDPC_SIGN_FMA
+    // Sign word on the FMA pipe (the check pass is bound by the ALU pipe): [Lq < 0] = sat(Lq * -inf)
+    // exactly -- -inf/+inf saturate to 0/1 and 0 * inf = NaN saturates to +0 -- accumulated as an exact
+    // small integer on top of 2^23, whose mantissa then holds the word.
+    float saccf = 8388608.0f;
+#pragma unroll
+    for (int k = 0; k < DEG; ++k) {
+        const float neg = __saturatef(__fmul_rn(q[k], __uint_as_float(0xff800000u)));
+        saccf = __fmaf_rn(neg, (float)(1u << (DEG - 1 - k)), saccf);  // sign of Lq on edge k -> bit DEG-1-k
+    }
+    const uint32_t sacc = __float_as_uint(saccf);
+#else
+    uint32_t sacc = 0;
+#pragma unroll
+    for (int k = 0; k < DEG; ++k) sacc = push_top_bit(sacc, __float_as_uint(q[k]));  // sign of Lq on edge k -> bit DEG-1-k
+#endif
+    // The argmin: an edge is "hot" when |Lq| == min1, i.e. min1 - |Lq| is +0 (never NaN for finite inputs),
+    // "cold" when it is negative.  Edges that tie at min1 make min2 == min1, so then ANY index gives the
+    // same messages.
+#if NRLDPC_COLD_FMA
+    // position of the hot edge = sum(all k) - sum(cold k), with cold = sat(d * -inf) in {0, 1} exactly and the
+    // sum kept as an exact small integer on top of 2^23, whose low mantissa bits are then the position
+    float hotpos = 8388608.0f + (float)(DEG * (DEG - 1) / 2);
+#pragma unroll
+    for (int k = 1; k < DEG; ++k) {
+        const float c = __saturatef(__fmul_rn(__fsub_rn(fabsf(m1), fabsf(q[k])), __uint_as_float(0xff800000u)));
+        hotpos = __fmaf_rn(c, -(float)k, hotpos);
+    }
+    const uint32_t kmin = __float_as_uint(hotpos);  // low bits; masked to the index field below
+#else
+    uint32_t cold = 0;
+#pragma unroll
+    for (int k = 0; k < DEG; ++k) cold = push_top_bit(cold, __float_as_uint(__fsub_rn(fabsf(m1), fabsf(q[k]))));
+    const uint32_t hot = ~cold & ALL;
+    const uint32_t kmin = (uint32_t)(DEG - 32) + (uint32_t)__clz(hot);  // DEG-1 - (31 - clz): smallest hot k
+#endif
+    // :199-202  Lr = alpha * sign_prod * sign(Lq) * max(minv - beta, 0), minv = min2 on the argmin edge
+    // (beta == 0: max(m - 0, 0) == m for m >= +0)
+    const float mag1 = B0 ? __fmul_rn(a.alpha, fabsf(m1)) : __fmul_rn(a.alpha, fmaxf(__fsub_rn(fabsf(m1), a.beta), 0.f));
+    const float mag2 = B0 ? __fmul_rn(a.alpha, m2) : __fmul_rn(a.alpha, fmaxf(__fsub_rn(m2, a.beta), 0.f));
+    const uint32_t sp = (uint32_t)((int)__float_as_uint(m1) >> 31);  // all ones when the sign product is -
+    const uint32_t nb = ((sacc ^ sp) & ALL) | ((kmin << C::idx_shift(I)) & C::idx_mask(I));
+    *reinterpret_cast<float *>(rec) = mag1;
+    *reinterpret_cast<float *>(rec + C::mag2_dist) = mag2;
+    store_bits<C, I>(bp, nb);
+    if (th.tile == 0) {  // mirror of the first 32 records behind the array (rotated reads of the variable pass)
+        *reinterpret_cast<float *>(rec + C::ZC * 4) = mag1;
+        *reinterpret_cast<float *>(rec + C::mag2_dist + C::ZC * 4) = mag2;
+        store_bits<C, I>(bp + C::ZC * 4, nb);
+    }
+    if (ET && (synd >> 31)) flag[0] = 1;
+}
+
+// Channel LLR of the degree-1 extension variable of row-block I (0 for the core rows), -0.0 -> +0.0.
+// (-0.0 -> +0.0 only when the syndrome reads the sign bit of LLR + Lr (ET); the messages do not depend on
+// the sign of a zero LLR: x = LLR + Lr and Lq = x - Lr give the same values either way.)
+template <class C, int I, bool ET> __device__ __forceinline__ float load_ext_llr(const Th<C> &th)
+{
+    if constexpr (I >= 4) {
+        const float v = __ldg(th.llr + (C::kb + I - 2) * C::ZC);
+        return ET ? __fadd_rn(v, 0.0f) : v;
+    } else return 0.f;
+}
+
+// The rows of warp group SUB, software-pipelined: the compiler cannot move a row's shared-memory loads
+// above the previous row's record stores (it cannot prove they do not alias), so the next row's inputs
+// are loaded, in program order, BEFORE the current row is computed and stored; its channel LLR (L2) too.
+// Rows whose combined degree exceeds NRLDPC_PF_SUM load their inputs after the store instead (registers).
+template <class C, bool ET, bool B0, int SUB, int O = 0>
+__device__ __forceinline__ void cn_pass_s(const DecArgs &a, const Th<C> &th, int *flag,
+                                          const RowIn<C, kRows<C>.item[SUB][O]> &in_cur, const float llr_cur)
+{
+    constexpr int I = kRows<C>.item[SUB][O];
+    if constexpr (O + 1 < kRows<C>.n[SUB]) {
+        constexpr int In = kRows<C>.item[SUB][O + 1];
+        const float llr_nxt = load_ext_llr<C, In, ET>(th);
+        if constexpr (C::deg(I) + C::deg(In) <= NRLDPC_PF_SUM) {
+            const RowIn<C, In> in_nxt = load_row<C, In>(th);
+            cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
+            cn_pass_s<C, ET, B0, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
+        } else {
+            cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
+            const RowIn<C, In> in_nxt = load_row<C, In>(th);
+            cn_pass_s<C, ET, B0, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
+        }
+    } else {
+        cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
+    }
+}
+
+template <class C, int J, int Nn>
+__device__ __forceinline__ void vn_entry_s(float &acc, const Th<C> &th)
+{
+    constexpr int e = C::cedge(J, Nn), i = C::row_of(e), k = e - C::G::rowptr(i), DEGI = C::deg(i);
+    constexpr int back = (C::ZC - C::P(e)) % C::ZC, t = C::wrap_tile(back);  // check r = (c - P) mod Zc
+    const uint32_t bits = load_bits<C, i>(th.smem + (C::bits_base(i) + 4 * back) + th.r4 + th.w4[t]);
+    const bool isidx = ((bits ^ ((uint32_t)k << C::idx_shift(i))) & C::idx_mask(i)) == 0;
+    // only the magnitude this edge uses is read (one 128-byte wavefront): mag2 on the argmin edge, mag1 elsewhere
+#if NRLDPC_VN_PSEL
+    const float mag = *reinterpret_cast<const float *>((isidx ? th.p4m2 : th.p4) + ((C::mags_base(i) + 4 * back) + th.w4[t]));
+#else
+    const float mag = *reinterpret_cast<const float *>(th.smem + (C::mags_base(i) + 4 * back) + (isidx ? th.r4m2 : th.r4) + th.w4[t]);
+#endif
+    acc = __fadd_rn(acc, __uint_as_float(__float_as_uint(mag) ^ ((bits << (31 - (DEGI - 1 - k))) & 0x80000000u)));
+}
+
+template <class C, int J, int... Nn>
+__device__ __forceinline__ void vn_entries_s(float &acc, const Th<C> &th, std::integer_sequence<int, Nn...>)
+{
+    (vn_entry_s<C, J, Nn>(acc, th), ...);
+}
+
+// One core variable of column-block J (compile time), lifted index c = r: LQ = LLRin + sum_i Lr(i) in
+// ascending row-block order = ascending check index (py5gphy/ldpc/nr_ldpc_decode.py:126).
+template <class C, int J>
+__device__ __forceinline__ float vn_col_s(const Th<C> &th_, const float lv)
+{
+    const Th<C> th = opaque(th_);
+    float acc = 0.f;
+    vn_entries_s<C, J>(acc, th, std::make_integer_sequence<int, C::cdeg(J)>{});
+    return __fadd_rn(lv, acc);
+}
+template <class C, int J>
+__device__ __forceinline__ void vn_store_s(const Th<C> &th, const float lq)
+{
+    float *dst = reinterpret_cast<float *>(th.smem + C::lq_base(J) + th.r4);
+    *dst = lq;
+    if (th.tile == 0) dst[C::ZC] = lq;  // mirror for the rotated reads of the check pass
+}
+
+// Channel LLR of core column-block J; the 2Zc punctured systematic bits start at LLR 0 (:43).
+// (no -0.0 -> +0.0 here: the sum of the messages is never -0.0, so LLR + sum has the same value and sign.)
+template <class C, int J> __device__ __forceinline__ float load_col_llr(const Th<C> &th)
+{
+    if constexpr (J >= 2) return __ldg(th.llr + (J - 2) * C::ZC);
+    else return 0.f;
+}
+
+// The columns of warp group SUB.  A column's posterior is stored after the NEXT column's records have
+// been read (same aliasing argument as in cn_pass_s), its channel LLR is fetched one column ahead.
+template <class C, int SUB, int O = 0>
+__device__ __forceinline__ void vn_pass_s(const Th<C> &th, const float lv_cur, const float lq_prev)
+{
+    if constexpr (O < kCols<C>.n[SUB]) {
+        float lv_nxt = 0.f;
+        if constexpr (O + 1 < kCols<C>.n[SUB]) lv_nxt = load_col_llr<C, kCols<C>.item[SUB][O + 1]>(th);
+        const float lq = vn_col_s<C, kCols<C>.item[SUB][O]>(th, lv_cur);
+        if constexpr (O > 0) vn_store_s<C, kCols<C>.item[SUB][O - 1]>(th, lq_prev);
+        vn_pass_s<C, SUB, O + 1>(th, lv_nxt, lq);
+    } else if constexpr (O > 0) {
+        vn_store_s<C, kCols<C>.item[SUB][O - 1]>(th, lq_prev);
+    }
+}
+
+// Final syndrome of row-block I with the post-loop tie rule LQ<=0 -> 1 (:134-143) + extension hard bits.
+template <class C, int I, int... K>
+__device__ __forceinline__ void final_edges_s(uint32_t &synd, const Th<C> &th, std::integer_sequence<int, K...>)
+{
+    ((synd ^= (load_lq_rot<C, C::G::rowptr(I) + K>(th) <= 0.f) ? 1u : 0u), ...);
+}
+template <class C, int I>
+__device__ __forceinline__ void final_row_s(const Th<C> &th, int *flag)
+{
+    constexpr int DEG = C::deg(I), NCORE = (I >= 4) ? DEG - 1 : DEG;
+    uint32_t synd = 0;
+    final_edges_s<C, I>(synd, th, std::make_integer_sequence<int, NCORE>{});
+    if constexpr (I >= 4) {
+        float2 m;
+        m.x = *reinterpret_cast<const float *>(th.smem + C::mags_base(I) + th.r4);
+        m.y = *reinterpret_cast<const float *>(th.smem + (C::mags_base(I) + C::mag2_dist) + th.r4);
+        const uint32_t bits = load_bits<C, I>(th.smem + C::bits_base(I) + th.r4);
+        const bool isidx = ((bits ^ ((uint32_t)(DEG - 1) << C::idx_shift(I))) & C::idx_mask(I)) == 0;
+        const float lr = record_lr(m, isidx, bits << 31);
+        const float x = __fadd_rn(__fadd_rn(__ldg(th.llr + (C::kb + I - 2) * C::ZC), 0.0f), lr);
+        const bool hb1 = x <= 0.f;
+        const uint32_t hb = __ballot_sync(0xffffffffu, hb1);
+        if ((th.r & 31) == 0) reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + th.tile] = hb;
+        synd ^= hb1 ? 1u : 0u;
+    }
+    if (synd) flag[0] = 1;
+}
+template <class C, int SUB, int O = 0>
+__device__ __forceinline__ void final_pass_s(const Th<C> &th, int *flag)
+{
+    if constexpr (O < kRows<C>.n[SUB]) {
+        final_row_s<C, kRows<C>.item[SUB][O]>(th, flag);
+        asm volatile("" ::: "memory");
+        final_pass_s<C, SUB, O + 1>(th, flag);
+    }
+}
+
+// run PASS<SUB> for the warp's group (sub is warp-uniform)
+template <class C, bool ET, bool B0, int SUB = 0>
+__device__ __forceinline__ void run_cn(int sub, const DecArgs &a, const Th<C> &th, int *flag)
+{
+    if constexpr (SUB < C::S) {
+        if (sub == SUB) cn_pass_s<C, ET, B0, SUB>(a, th, flag, load_row<C, kRows<C>.item[SUB][0]>(th), load_ext_llr<C, kRows<C>.item[SUB][0], ET>(th));
+        else run_cn<C, ET, B0, SUB + 1>(sub, a, th, flag);
+    }
+}
+template <class C, int SUB = 0>
+__device__ __forceinline__ void run_vn(int sub, const Th<C> &th)
+{
+    if constexpr (SUB < C::S) {
+        if (sub == SUB) vn_pass_s<C, SUB>(th, load_col_llr<C, kCols<C>.item[SUB][0]>(th), 0.f);
+        else run_vn<C, SUB + 1>(sub, th);
+    }
+}
+template <class C, int SUB = 0>
+__device__ __forceinline__ void run_final(int sub, const Th<C> &th, int *flag)
+{
+    if constexpr (SUB < C::S) {
+        if (sub == SUB) final_pass_s<C, SUB>(th, flag);
+        else run_final<C, SUB + 1>(sub, th, flag);
+    }
+}
+
+// Pull `bytes` (a multiple of 16) at a 16-byte aligned global address into L2, asynchronously.
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+int num_sms()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <class C, bool ET, bool B0>
+__global__ void __launch_bounds__(C::nwarps * 32, 1)
+decode_spec_kernel(const __grid_constant__ DecArgs a)
+{
+    extern __shared__ __align__(16) char smem[];
+    __shared__ int s_flag[2];
+    constexpr int NT = C::nwarps * 32, ZC = C::ZC;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __reduce_min_sync(0xffffffffu, tid >> 5);  // warp-uniform (REDUX writes a uniform register)
+#if NRLDPC_SUB_INTERLEAVE
+    // warp -> (tile, group) with the group in the low bits: the warps of one scheduler (warp % 4) then all
+    // run the same instruction stream (S = 2: even schedulers group 0, odd schedulers group 1)
+    const int sub = warp % C::S;
+    Th<C> th;
+    th.smem = smem;
+    th.tile = warp / C::S;
+#else
+    const int sub = warp / C::tiles;
+    Th<C> th;
+    th.smem = smem;
+    th.tile = warp % C::tiles;
+#endif
+    th.r = th.tile * 32 + lane;
+    th.r4 = (uint32_t)th.r * 4u;
+    th.r4m2 = th.r4 + (uint32_t)C::mag2_dist;
+    th.p4 = smem + th.r4;
+    th.p4m2 = smem + th.r4m2;
+#pragma unroll
+    for (int t = 0; t <= C::tiles; ++t) th.w4[t] = (th.tile >= t) ? -4 * ZC : 0;
+
+    // Persistent CTA (one per SM: the codeblock state fills shared memory): codeblocks blockIdx.x,
+    // blockIdx.x + gridDim.x, ...  The channel LLRs are read straight from global memory every iteration
+    // (L2 hits); the NEXT codeblock's row is pulled into L2 while the current one is decoded, so that no
+    // HBM latency is exposed at a codeblock boundary.
+    const bool pf = tid == 0 && (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0;  // bulk prefetch needs 16-byte alignment
+    if (pf) prefetch_l2(a.llr + (size_t)blockIdx.x * C::N, C::N * 4);
+    for (int cb = blockIdx.x; cb < a.B; cb += gridDim.x) {
+        th.llr = a.llr + (size_t)cb * C::N + th.r;
+        if (pf && cb + (int)gridDim.x < a.B) prefetch_l2(a.llr + (size_t)(cb + gridDim.x) * C::N, C::N * 4);
+
+        // ---- init: records = 0 (Lr = 0, :101), LQ = LLRin (:94) with the punctured columns at 0 (:43)
+        {
+            constexpr int z0 = C::off_mags / 16, z1 = C::smem_bytes / 16;
+            static_assert(C::off_mags % 16 == 0 && C::smem_bytes % 16 == 0, "16-byte zero fill");
+            for (int t = z0 + tid; t < z1; t += NT) reinterpret_cast<uint4 *>(smem)[t] = make_uint4(0, 0, 0, 0);
+            for (int t = tid; t < 2 * C::LQS; t += NT) reinterpret_cast<float *>(smem + C::lq_base(0))[t] = 0.f;
+            if (tid < 2) s_flag[tid] = 0;
+            for (int j = 2 + sub; j < C::ncore; j += C::S) {
+                const float v = __fadd_rn(__ldg(th.llr + (j - 2) * ZC), 0.0f);  // -0.0 -> +0.0
+                float *dst = reinterpret_cast<float *>(smem + C::lq_base(j) + th.r4);
+                *dst = v;
+                if (th.tile == 0) dst[ZC] = v;
+            }
+        }
+        __syncthreads();
+
+        bool et_done = false;
+        int it = 0;
+        for (; it < a.max_iter; ++it) {
+            int *flag = &s_flag[it & 1];
+#ifndef NRLDPC_EXP_NO_CN
+            run_cn<C, ET, B0>(sub, a, th, flag);
+#endif
+            __syncthreads();
+            if (ET) {
+                if (*flag == 0) { et_done = true; break; }  // all parity checks hold for the current decisions (:111-114)
+                if (tid == 0) s_flag[(it + 1) & 1] = 0;
+            }
+#ifndef NRLDPC_EXP_NO_VN
+            run_vn<C>(sub, th);
+#endif
+            __syncthreads();
+        }
+        bool ok = et_done;
+        if (!et_done) {
+            int *flag = &s_flag[it & 1];
+            run_final<C>(sub, th, flag);
+            __syncthreads();
+            ok = (*flag == 0);
+        }
+
+        // ---- outputs
+        if (tid == 0) {
+            if (a.status) a.status[cb] = ok ? 1 : 0;
+            if (a.iters) a.iters[cb] = it;
+        }
+        const uint32_t *ext = reinterpret_cast<const uint32_t *>(smem + C::off_ext);
+        if (a.ck) {
+            int8_t *out = a.ck + (size_t)cb * C::Nfull;
+            for (int j = 0; j < C::ncore; ++j) {
+                const float *LQ = reinterpret_cast<const float *>(smem + C::lq_base(j));
+                for (int c = tid; c < ZC; c += NT) out[j * ZC + c] = (int8_t)(et_done ? (LQ[c] < 0.f) : (LQ[c] <= 0.f));
+            }
+            for (int n = tid; n < (C::nrows - 4) * ZC; n += NT) {
+                const int i4 = n / ZC, r = n - i4 * ZC;
+                out[C::ncore * ZC + n] = (int8_t)((ext[i4 * C::tiles + (r >> 5)] >> (r & 31)) & 1u);
+            }
+        }
+        if (a.info) {
+            constexpr int nwords = C::K / 32;  // K = kb * Zc, Zc a multiple of 32
+            for (int w = (tid >> 5); w < nwords; w += C::nwarps) {
+                const int n = 32 * w + lane, j = n / ZC, c = n - j * ZC;
+                const float x = *reinterpret_cast<const float *>(smem + C::lq_base(j) + 4 * c);
+                const uint32_t word = __ballot_sync(0xffffffffu, et_done ? (x < 0.f) : (x <= 0.f));
+                if (lane == 0) a.info[(size_t)cb * nwords + w] = word;
+            }
+        }
+        __syncthreads();  // the state is re-initialised for the next codeblock
+    }
+}
+
+template <class C>
+int launch_spec(const DecArgs &a, int early_term, cudaStream_t s)
+{
+    static_assert(C::smem_bytes <= 227 * 1024 - 64, "codeblock state does not fit in shared memory");
+    auto launch = [&](auto kern) -> int {
+        NRLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
+        kern<<<std::min(a.B, num_sms()), C::nwarps * 32, C::smem_bytes, s>>>(a);
+        NRLDPC_CUDA(cudaGetLastError());
+        return NRLDPC_OK;
+    };
+    if (a.beta == 0.f) return early_term ? launch(decode_spec_kernel<C, true, true>) : launch(decode_spec_kernel<C, false, true>);
+    return early_term ? launch(decode_spec_kernel<C, true, false>) : launch(decode_spec_kernel<C, false, false>);
+}
+
+}  // namespace
+
+
+// One instantiation per translation unit.
+#define NRLDPC_SPEC_INSTANCE(BGN, ZC)                                                                              \
+    int launch_decode_spec_##BGN##_##ZC(const DecArgs &a, int early_term, cudaStream_t s)                          \
+    {                                                                                                              \
+        return launch_spec<Code<BGN, ZC>>(a, early_term, s);                                                       \
+    }                                                                                                              \
+    void decode_spec_geometry_##BGN##_##ZC(int *threads, int *smem)                                                \
+    {                                                                                                              \
+        if (threads) *threads = Code<BGN, ZC>::nwarps * 32;                                                        \
+        if (smem) *smem = Code<BGN, ZC>::smem_bytes;                                                               \
+    }
+
+}  // namespace nrldpc

@@ -78,6 +78,13 @@ def encode_batch(ck, bgn, Zc=None, fix_fillers=True):
 
 # ------------------------------------------------------------------ min-sum decoder
 
+def decode_geometry(bgn, Zc):
+    """(codeblocks per CTA, threads, dynamic shared memory bytes) of the kernel decode_batch launches for (bgn, Zc)."""
+    G, nt, smem = (ctypes.c_int() for _ in range(3))
+    _lib.check(_lib.lib().nrldpc_decode_minsum_geometry(int(bgn), int(Zc), G, nt, smem), "decode_geometry")
+    return G.value, nt.value, smem.value
+
+
 def decode_batch(llr, Zc, bgn, L, alpha=1.0, beta=0.0, early_term=True, want_ck=True, want_info=False):
     """nr_decode_ldpc(..., 'min-sum', alpha, beta) for B codeblocks in fp32
     (py5gphy/ldpc/nr_ldpc_decode.py:11-49,51-143,178-227).

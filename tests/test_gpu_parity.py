@@ -164,18 +164,20 @@ def test_decode_all_lifting_sizes_vs_oracle(eng, oracle, bgn):
     assert diff64 <= max(0, int(tot * 1e-4)), (diff64, tot)
 
 
-def test_decode_headline_spec_kernel_vs_oracle(eng, oracle):
-    """BG1 Zc=384 goes through the compile-time specialised kernel (nrldpc_decode_spec.cu): bit-exact
+@pytest.mark.parametrize("bgn,Zc", [(1, 384), (2, 384), (1, 352), (2, 352)])
+def test_decode_headline_spec_kernel_vs_oracle(eng, oracle, bgn, Zc):
+    """These (bgn, Zc) go through the compile-time specialised kernels (nrldpc_decode_spec.cuh): bit-exact
     against the fp32 restatement for NMS / OMS / mixed / plain min-sum, with and without early
     termination, at SNRs where blocks converge early, late and not at all; a batch larger than one
     wave of persistent CTAs; ties, zeros and -0.0 inputs."""
-    bgn, Zc = 1, 384
+    assert eng.decode_geometry(bgn, Zc)[0] == 1   # one codeblock per persistent CTA = the specialised kernel
     K, N, Nf, M = eng.dims(bgn, Zc)
-    rng = np.random.default_rng(384)
+    rng = np.random.default_rng(Zc + bgn)
     ck = _rand_ck(rng, bgn, Zc, 40, fillers=False)
     dn = oracle.encode_batch(ck.copy(), bgn, Zc)
-    cases = [(-3.0, 6, 0.8, 0.0, 1), (0.4, 10, 0.8, 0.0, 1), (0.4, 10, 0.8, 0.0, 0), (0.6, 12, 1.0, 0.5, 1),
-             (0.6, 9, 0.8, 0.3, 0), (1.5, 10, 1.0, 0.0, 1), (0.2, 16, 0.7, 0.0, 1)]
+    o = 0.0 if bgn == 1 else -2.6   # BG2 (rate 1/5) works ~2.6 dB lower
+    cases = [(-3.0 + o, 6, 0.8, 0.0, 1), (0.4 + o, 10, 0.8, 0.0, 1), (0.4 + o, 10, 0.8, 0.0, 0), (0.6 + o, 12, 1.0, 0.5, 1),
+             (0.6 + o, 9, 0.8, 0.3, 0), (1.5 + o, 10, 1.0, 0.0, 1), (0.2 + o, 16, 0.7, 0.0, 1)]
     for ci, (snr, L, alpha, beta, et) in enumerate(cases):
         sel = slice(5 * ci, 5 * ci + 10)
         llr = _awgn(rng, dn[sel], snr)
@@ -197,7 +199,7 @@ def test_decode_headline_spec_kernel_vs_oracle(eng, oracle):
     # more codeblocks than persistent CTAs (the kernel loops over codeblocks): replicate a small set and
     # compare every copy with the first one
     import torch
-    base = torch.from_numpy(_awgn(rng, dn[:8], 0.5)).cuda()
+    base = torch.from_numpy(_awgn(rng, dn[:8], 0.5 + o)).cuda()
     big = base.repeat(40, 1).contiguous()   # 320 codeblocks > 148 SMs
     r = eng.decode_batch(big, Zc, bgn, 10, 0.8, 0.0, True)
     torch.cuda.synchronize()
