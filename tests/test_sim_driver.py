@@ -120,3 +120,29 @@ def test_gpu_driver_device_rng_bler_in_ci():
                                           rng="device", verbose=False)
     assert 0.20 < table[0][0] < 0.36
     assert table[0][1] < 0.012
+
+
+# BLER values of the reference's shipped tables (out/NMS_search_alpha_*, out/OMS_search_beta_*):
+# (Zc, bgn, algo, parameter, L, snr_db, shipped BLER).  The reference's trial count per point is not stored
+# (granularity suggests 400-2000): the check uses n_ref = 400 for its binomial interval.
+SHIPPED_BLER = [
+    (12, 1, 'NMS', 0.5, 32, -0.5, 0.19), (12, 1, 'NMS', 0.7, 32, -0.5, 0.085), (12, 1, 'NMS', 0.9, 32, -0.5, 0.405),
+    (72, 1, 'NMS', 0.5, 32, -0.5, 0.02), (72, 1, 'NMS', 0.9, 32, -0.5, 0.35), (28, 2, 'NMS', 0.3, 32, -0.5, 0.425),
+    (208, 1, 'NMS', 0.9, 32, -0.5, 0.145), (384, 1, 'NMS', 0.9, 32, -0.5, 0.115), (384, 1, 'NMS', 0.5, 32, -0.5, 0.05),
+    (12, 1, 'OMS', 0.3, 16, -0.5, 0.245), (40, 1, 'OMS', 0.9, 16, -0.5, 0.285), (176, 1, 'OMS', 0.1, 16, -0.5, 0.685),
+]
+
+
+@pytest.mark.gpu
+def test_gpu_bler_matches_shipped_tables():
+    """BLER-vs-SNR points of the reference's own parameter-search runs, re-run with device-generated inputs
+    (the reference's stopping rule: 1000-10000 codeblocks per point), inside a 4-sigma binomial interval."""
+    from python_5gtoolbox_b200 import sim
+    for Zc, bgn, algo, par, L, snr, ref in SHIPPED_BLER:
+        alpha, beta = ([par], []) if algo == 'NMS' else ([], [par])
+        _, _, table = sim.run_ldpc_simulation(Zc, bgn, '24A', [algo], alpha, beta, [], [L], [snr], None, rng="device",
+                                              verbose=False)
+        p = table[0][0]
+        n = 10000 if p < 0.0025 else (4000 if p < 0.00625 else (2000 if p < 0.025 else 1000))  # the stopping rule's n
+        tol = 4 * (ref * (1 - ref) / 400 + p * (1 - p) / n) ** 0.5 + 0.005
+        assert abs(p - ref) <= tol, (Zc, bgn, algo, par, p, ref, tol)
