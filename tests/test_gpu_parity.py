@@ -164,7 +164,7 @@ def test_decode_all_lifting_sizes_vs_oracle(eng, oracle, bgn):
     assert diff64 <= max(0, int(tot * 1e-4)), (diff64, tot)
 
 
-@pytest.mark.parametrize("bgn,Zc", [(1, 384), (2, 384), (1, 352), (2, 352)])
+@pytest.mark.parametrize("bgn,Zc", [(1, 384), (2, 384), (1, 352), (2, 352), (1, 320), (2, 320), (1, 288), (2, 288)])
 def test_decode_headline_spec_kernel_vs_oracle(eng, oracle, bgn, Zc):
     """These (bgn, Zc) go through the compile-time specialised kernels (nrldpc_decode_spec.cuh): bit-exact
     against the fp32 restatement for NMS / OMS / mixed / plain min-sum, with and without early
