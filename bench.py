@@ -266,6 +266,15 @@ def run_ours(args):
                                  "wavefronts; see DESIGN.md and profiles/"},
             "clocks": clk.summary(),
         }
+        # the roof that actually binds: warp-instruction issue slots (148 SMs x 4 schedulers x SM clock)
+        clk_mhz = out["clocks"].get("sm_mhz") or 1965
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sms * 4 * clk_mhz * 1e6
+        out["roofline_onchip"] = {"bound": "issue_slots", "achieved": per_gpu_cbs * WARP_INSTR_PER_CB / 1e9,
+                                  "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": per_gpu_cbs * WARP_INSTR_PER_CB / issue_peak,
+                                  "warp_instr_per_codeblock": WARP_INSTR_PER_CB,
+                                  "source": "smsp__inst_executed.sum of profiles/prof_r1h.ncu-rep / 592 codeblocks; ALU pipe 74 %, "
+                                            "issue 81 %, smem wavefronts 63 % busy in that capture"}
         if not args.no_cpu and world == 1:   # reported at N=1 only (rank 0); ~10 s of CPU work on all host cores
             ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             gbps, threads, n, sps = cpu_reference_run(1, 0, sample_cbs=max(400 * ncores, 256))
@@ -282,9 +291,10 @@ def ctypes_int():
     return ctypes.c_int()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per codeblock from the committed `ncu --set full` capture
-# (profiles/r1_decode_spec_ncu_summary.md: 60.160 MB + 0.362 MB for 592 codeblocks)
-TRAFFIC_BYTES_PER_CB = (60160000 + 361728) / 592
+# From the committed `ncu --set full` capture (profiles/r1_decode_spec_ncu_summary.md, 592 codeblocks):
+# dram__bytes_read.sum + dram__bytes_write.sum = 60.151 MB + 0.292 MB; smsp__inst_executed.sum = 495.07 M
+TRAFFIC_BYTES_PER_CB = (60151296 + 291840) / 592
+WARP_INSTR_PER_CB = 495071248 / 592
 
 
 def main():
