@@ -1,4 +1,5 @@
 // nrldpc_api.cu -- the extern "C" boundary of libnrldpc_b200.so (see include/nrldpc_b200.h).
+#include <array>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -242,9 +243,11 @@ int nrldpc_decode_minsum_geometry(int bgn, int Zc, int *cbs_per_cta, int *thread
     return decode_minsum_geometry(*c, cbs_per_cta, threads, smem_bytes);
 }
 
-// Host-buffer entry point: double-buffered chunks so that (with pinned host memory) the H2D copy of
-// chunk i+1 and the D2H copy of chunk i-1 overlap the decode of chunk i.  The two stages' device
-// buffers and streams are created once per device and reused (grow-only) by later calls.
+// Host-buffer entry point: a ring of kHostStages chunks so that (with pinned host memory) the H2D copy of
+// chunk i+1 and the D2H copy of chunk i-1 overlap the decode of chunk i.  The stages' device buffers and
+// streams are created once per device and reused (grow-only) by later calls.  The path is bound by the
+// host link (101 KB of LLRs per codeblock), so the chunks are kept small: the only exposed time is the
+// first chunk's copy and the last chunk's decode.
 namespace {
 struct HostStage {
     void *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // llr, ck, info, status, iters
@@ -259,9 +262,11 @@ struct HostStage {
         return NRLDPC_OK;
     }
 };
+constexpr int kHostStages = 3;
+constexpr size_t kHostChunkBytes = (size_t)32 << 20;
 struct HostPipe {
     std::mutex mu;
-    std::map<int, std::pair<HostStage, HostStage>> per_device;
+    std::map<int, std::array<HostStage, kHostStages>> per_device;
 };
 HostPipe g_pipe;
 }  // namespace
@@ -276,12 +281,13 @@ int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_
     int dev = 0;
     NRLDPC_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_pipe.mu);
-    auto &pair = g_pipe.per_device[dev];
-    HostStage *st[2] = {&pair.first, &pair.second};
+    auto &ring = g_pipe.per_device[dev];
+    HostStage *st[kHostStages];
+    for (int i = 0; i < kHostStages; ++i) st[i] = &ring[i];
     const size_t llr_bytes = (size_t)c->N * 4, nwords = (size_t)(c->K + 31) / 32;
-    int chunk = (int)std::max<size_t>(1, ((size_t)128 << 20) / llr_bytes);
+    int chunk = (int)std::max<size_t>(1, kHostChunkBytes / llr_bytes);
     if (chunk > B) chunk = (B + 1) / 2 > 256 ? (B + 1) / 2 : B;  // two chunks still overlap copy and compute
-    const int nstage = B > chunk ? 2 : 1;
+    const int nstage = std::min(kHostStages, (B + chunk - 1) / chunk);
     for (int i = 0; i < nstage; ++i) {
         if (!st[i]->s) NRLDPC_CUDA(cudaStreamCreateWithFlags(&st[i]->s, cudaStreamNonBlocking));
         if (int rc = st[i]->ensure(0, (size_t)chunk * llr_bytes)) return rc;
