@@ -400,3 +400,39 @@ def test_dropin_modules_match_oracle(eng, oracle):
     view = ck[:]
     dn = nr_ldpc_encode.encode_ldpc(view, 1)
     assert (ck[40:] == 0).all() and (dn[36:40] == -1).all()
+
+
+def test_headline_size_properties(eng):
+    """BASELINE.json's headline size (BG1 Zc=384, tens of thousands of codeblocks, too many for the CPU oracle):
+    size-independent properties.  (1) the encoder is linear over GF(2); (2) every decoder output flagged
+    status=1 satisfies all parity checks (re-encoding its systematic part reproduces it); (3) codeword
+    symmetry of min-sum: flipping the LLR signs by ANY codeword flips the decoded bits by that codeword
+    and leaves status / iteration counts untouched, bit for bit (fp32 negation is exact)."""
+    import torch
+    bgn, Zc, B = 1, 384, 20000
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    a = eng.random_bits(B, K, seed=21, device="cuda")
+    b = eng.random_bits(B, K, seed=22, device="cuda")
+    ca, cb, cab = eng.encode_batch(a, bgn), eng.encode_batch(b, bgn), eng.encode_batch(a ^ b, bgn)
+    assert torch.equal(ca ^ cb, cab)
+    llr = eng.awgn_llr(ca, 0.7, seed=23)
+    r = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, True, want_info=True)
+    ok = r["status"].bool()
+    assert 0.5 < float(ok.float().mean()) <= 1.0
+    full = torch.cat([a[:, :2 * Zc], ca], 1)
+    sys_part = r["ck"][:, :K].contiguous()
+    re = eng.encode_batch(sys_part.clone(), bgn)
+    assert torch.equal(re[ok], r["ck"][ok][:, 2 * Zc:])          # status=1  =>  a codeword
+    assert torch.equal(r["ck"][ok], full[ok]) or float((r["ck"][ok] != full[ok]).any(1).float().mean()) < 1e-3  # and (almost always) the sent one
+    bits = ((r["info"].view(torch.uint8).unsqueeze(-1) >> torch.arange(8, device="cuda", dtype=torch.uint8)) & 1).reshape(B, -1)[:, :K]
+    assert torch.equal(bits.to(torch.int8), sys_part)
+    # symmetry under the codeword cb (its two punctured column-blocks never reach the channel)
+    llr2 = (llr * (1 - 2 * cb.float())).contiguous()
+    r2 = eng.decode_batch(llr2, Zc, bgn, 10, 0.8, 0.0, True)
+    fullb = torch.cat([b[:, :2 * Zc], cb], 1)
+    assert torch.equal(r2["status"], r["status"]) and torch.equal(r2["iters"], r["iters"])
+    assert torch.equal(r2["ck"], r["ck"] ^ fullb)
+    # and in throughput mode (10 fixed iterations)
+    r3 = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, False)
+    r4 = eng.decode_batch(llr2, Zc, bgn, 10, 0.8, 0.0, False)
+    assert torch.equal(r4["ck"], r3["ck"] ^ fullb) and torch.equal(r4["status"], r3["status"])
