@@ -72,10 +72,12 @@ constexpr int ils_of(int Zc)
 template <int BGN, int ZC_> struct Code {
     using G = Graph<BGN>;
     static constexpr int bgn = BGN, ZC = ZC_, iLS = ils_of(ZC_);
-    static_assert(iLS >= 0 && ZC_ % 32 == 0, "specialised kernels need a lifting size that is a multiple of 32");
+    // Any lifting size >= 64: r-tile 0 must be full (it writes the 32 mirrored elements).  In a partial last
+    // tile the lanes beyond Zc duplicate lane Zc-1 (same loads, same stores of the same values).
+    static_assert(iLS >= 0 && ZC_ >= 64, "specialised kernels need a lifting size >= 64");
     static constexpr int nrows = G::rows, kb = G::kb, ncore = G::kb + 4, nnz = G::nnz;
     static constexpr int K = kb * ZC, N = (G::cols - 2) * ZC, Nfull = G::cols * ZC;
-    static constexpr int tiles = ZC / 32, S = (32 / tiles) < kMaxS ? (32 / tiles) : kMaxS, nwarps = tiles * S;
+    static constexpr int tiles = (ZC + 31) / 32, S = (32 / tiles) < kMaxS ? (32 / tiles) : kMaxS, nwarps = tiles * S;
     static constexpr int LQS = ZC + 32;  // elements per rotated array: Zc + the 32 mirrored ones
     static constexpr int deg(int i) { return G::rowptr(i + 1) - G::rowptr(i); }
     static constexpr int P(int e) { return G::shift(iLS, e) % ZC; }
@@ -102,7 +104,7 @@ template <int BGN, int ZC_> struct Code {
     // shared-memory layout (bytes)
     static constexpr int off_lq = 0;                                          // float LQ[ncore][LQS]
     static constexpr int off_mags = off_lq + ncore * LQS * 4;                 // float mag1[nrows][LQS], then mag2[nrows][LQS]
-    static constexpr int mag2_dist = nrows * LQS * 4;                         // bytes from a row's mag1 to its mag2 (multiple of 128: same banks)
+    static constexpr int mag2_dist = (nrows * LQS * 4 + 127) & ~127;          // bytes from a row's mag1 to its mag2 (multiple of 128: same banks)
     static constexpr int off_b32 = off_mags + 2 * mag2_dist;                  // uint32 [count(2)][LQS]
     static constexpr int off_b16 = off_b32 + count(2) * LQS * 4;              // uint16 pairs of rows interleaved
     static constexpr int off_b8 = off_b16 + ((count(1) + 1) / 2) * LQS * 4;   // uint8 quads of rows interleaved
@@ -535,7 +537,7 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     th.smem = smem;
     th.tile = warp % C::tiles;
 #endif
-    th.r = th.tile * 32 + lane;
+    th.r = min(th.tile * 32 + lane, ZC - 1);
     th.r4 = (uint32_t)th.r * 4u;
     th.r4m2 = th.r4 + (uint32_t)C::mag2_dist;
     th.p4 = smem + th.r4;
@@ -612,11 +614,12 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
             }
         }
         if (a.info) {
-            constexpr int nwords = C::K / 32;  // K = kb * Zc, Zc a multiple of 32
+            constexpr int nwords = (C::K + 31) / 32;
             for (int w = (tid >> 5); w < nwords; w += C::nwarps) {
-                const int n = 32 * w + lane, j = n / ZC, c = n - j * ZC;
+                const int n = min(32 * w + lane, C::K - 1), j = n / ZC, c = n - j * ZC;
                 const float x = *reinterpret_cast<const float *>(smem + C::lq_base(j) + 4 * c);
-                const uint32_t word = __ballot_sync(0xffffffffu, et_done ? (x < 0.f) : (x <= 0.f));
+                uint32_t word = __ballot_sync(0xffffffffu, et_done ? (x < 0.f) : (x <= 0.f));
+                if (32 * w + 32 > C::K) word &= (1u << (C::K - 32 * w)) - 1u;   // last, partial word
                 if (lane == 0) a.info[(size_t)cb * nwords + w] = word;
             }
         }

@@ -164,7 +164,8 @@ def test_decode_all_lifting_sizes_vs_oracle(eng, oracle, bgn):
     assert diff64 <= max(0, int(tot * 1e-4)), (diff64, tot)
 
 
-@pytest.mark.parametrize("bgn,Zc", [(1, 384), (2, 384), (1, 352), (2, 352), (1, 320), (2, 320), (1, 288), (2, 288)])
+@pytest.mark.parametrize("bgn,Zc", [(1, 384), (2, 384), (1, 352), (2, 352), (1, 320), (2, 320), (1, 288), (2, 288),
+                                    (1, 208), (2, 208), (1, 176), (2, 176)])
 def test_decode_headline_spec_kernel_vs_oracle(eng, oracle, bgn, Zc):
     """These (bgn, Zc) go through the compile-time specialised kernels (nrldpc_decode_spec.cuh): bit-exact
     against the fp32 restatement for NMS / OMS / mixed / plain min-sum, with and without early
@@ -201,9 +202,9 @@ def test_decode_headline_spec_kernel_vs_oracle(eng, oracle, bgn, Zc):
     import torch
     base = torch.from_numpy(_awgn(rng, dn[:8], 0.5 + o)).cuda()
     big = base.repeat(40, 1).contiguous()   # 320 codeblocks > 148 SMs
-    r = eng.decode_batch(big, Zc, bgn, 10, 0.8, 0.0, True)
+    r = eng.decode_batch(big, Zc, bgn, 10, 0.8, 0.0, True, want_info=True)
     torch.cuda.synchronize()
-    for key in ("ck", "status", "iters"):
+    for key in ("ck", "status", "iters", "info"):
         v = r[key].reshape(40, 8, -1)
         assert torch.equal(v, v[:1].expand_as(v)), key
     c, s, i = oracle.decode_batch(base.cpu().numpy(), Zc, bgn, 10, "min-sum", 0.8, 0.0, 1, np.float32)
