@@ -6,16 +6,23 @@
 // graph is unrolled at compile time from the constexpr TS 38.212 tables, so every shift, column offset,
 // record offset and sign-bit position is an immediate and each warp group runs straight-line code.
 //
-// The kernel is bound by the SM's ALU pipe (LOP3/SHF/FMNMX/ISETP/SEL issue at half rate), not by HBM or
-// shared memory, so the design removes ALU instructions from the per-edge path:
+// One persistent CTA per SM decodes one codeblock at a time with its whole state in shared memory (see
+// DESIGN.md 3-4).  HBM sees 4N + K/8 bytes per codeblock and is ~1 % busy; the kernel is bound by warp
+// instruction issue and the half-rate ALU pipe (LOP3/SHF/FMNMX/ISETP/SEL), so the design is about
+// instructions per edge:
 //   * circulant shifts cost no instruction: every shared-memory array that is read through a rotation
 //     (posteriors LQ in the check pass, row records in the variable pass) carries 32 extra elements that
 //     mirror its first 32, and the (r + P) mod Zc wrap becomes a WARP-UNIFORM choice between offset 0
-//     and -Zc (tile >= ceil((Zc-P)/32)), held in uniform registers: LDS [R + UR + imm];
-//   * the argmin of a check row is found after the two minima are known, from the sign of
-//     (min1 - |Lq|) computed on the FMA pipe, instead of a compare + select per edge;
+//     and -Zc (tile >= ceil((Zc-P)/32)): LDS [R + UR + imm] or a per-lane base pre-added once;
+//   * the argmin of a check row is found after the two minima are known, on the FMA pipe:
+//     sat((min1 - |Lq|) * -inf) is exactly 1 on every edge but the minimum one;
 //   * sign/argmin words are 8-bit for rows of degree <= 5, 16-bit up to degree 12 and 32-bit above,
-//     interleaved so that all of them have a 4-byte stride (one set of wrap offsets, no bank conflicts).
+//     interleaved so that all of them have a 4-byte stride (one set of wrap offsets, no bank conflicts);
+//   * the two magnitudes of a row live in separate arrays a multiple of 128 B apart: the variable pass
+//     selects the address and reads ONE 128-byte wavefront per edge;
+//   * rows / columns are software-pipelined by hand across the record stores (the compiler cannot prove
+//     that the shared-memory stores of one row do not alias the loads of the next).
+// Compile-time switches (NRLDPC_*) keep the measured alternatives buildable: tools/build_variant.sh.
 #pragma once
 #include <algorithm>
 #include <cstdlib>
