@@ -129,6 +129,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     seed = 0x5601 + rank
