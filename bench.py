@@ -129,8 +129,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the JSON line only: NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) to fd 1
+        # when the communicator is created, so fd 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B = args.batch
     seed = 0x5601 + rank
 
