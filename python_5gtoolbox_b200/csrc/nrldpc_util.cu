@@ -127,6 +127,69 @@ __global__ void crc_kernel(const int8_t *__restrict__ in, int B, int A, int L, u
     }
 }
 
+// ---- the same CRC for long blocks (transport blocks of up to ~10^6 bits): one CTA per block of bits.
+// The CRC is linear over GF(2): with the message cut into chunks, M(x) = sum_t chunk_t(x) x^{s_t}
+// (s_t = message bits after chunk t), so  M(x) x^L mod P = sum_t (r_t * x^{s_t}) mod P  with r_t the CRC of
+// chunk t alone.  Each thread runs the bit-serial register over its own chunk, multiplies by x^{s_t} mod P
+// (square-and-multiply in GF(2)[x]/P, ~40 L-step products) and the partial remainders are XOR-reduced.
+constexpr int kCrcBlockThreads = 256;
+
+__device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b, int L, uint32_t poly, uint32_t mask)
+{
+    uint32_t res = 0;
+    for (int i = L - 1; i >= 0; --i) {
+        const uint32_t top = (res >> (L - 1)) & 1u;
+        res = (res << 1) & mask;
+        if (top) res ^= poly;
+        if ((b >> i) & 1u) res ^= a;
+    }
+    return res;
+}
+
+__global__ void __launch_bounds__(kCrcBlockThreads)
+crc_block_kernel(const int8_t *__restrict__ in, int A, int L, uint32_t poly, int mode, int8_t *__restrict__ out,
+                 uint8_t *__restrict__ err)
+{
+    __shared__ uint32_t s_part[kCrcBlockThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int len_in = mode ? A + L : A;
+    const int8_t *x = in + (size_t)b * len_in;
+    const uint32_t mask = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+    const int chunk = (A + kCrcBlockThreads - 1) / kCrcBlockThreads;
+    const int k0 = min(tid * chunk, A), k1 = min(k0 + chunk, A);
+    uint32_t rem = 0;
+    for (int k = k0; k < k1; ++k) {  // chunk(x) * x^L mod P
+        const uint32_t fb = ((rem >> (L - 1)) & 1u) ^ (uint32_t)(x[k] & 1);
+        rem = (rem << 1) & mask;
+        if (fb) rem ^= poly;
+    }
+    if (rem) {  // times x^(A - k1) mod P
+        uint32_t e = (uint32_t)(A - k1), base = 2u, acc = 1u;
+        while (e) {
+            if (e & 1u) acc = gf2_mulmod(acc, base, L, poly, mask);
+            base = gf2_mulmod(base, base, L, poly, mask);
+            e >>= 1;
+        }
+        rem = gf2_mulmod(rem, acc, L, poly, mask);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, o);
+    if (lane == 0) s_part[tid >> 5] = rem;
+    __syncthreads();
+    rem = 0;
+#pragma unroll
+    for (int w = 0; w < kCrcBlockThreads / 32; ++w) rem ^= s_part[w];
+    if (mode == 0) {
+        int8_t *y = out + (size_t)b * (A + L);
+        for (int k = tid; k < A; k += kCrcBlockThreads) y[k] = x[k];
+        if (tid < L) y[A + tid] = (int8_t)((rem >> (L - 1 - tid)) & 1u);
+    } else if (tid == 0) {
+        uint32_t got = 0;
+        for (int k = 0; k < L; ++k) got = (got << 1) | (uint32_t)(x[A + k] & 1);
+        err[b] = rem != got;
+    }
+}
+
 }  // namespace
 
 }  // namespace nrldpc
@@ -201,13 +264,17 @@ static int crc_poly(int poly_id, int *L, uint32_t *poly)
     return NRLDPC_OK;
 }
 
+// long blocks, or too few blocks to fill the GPU with one thread each: one CTA per block of bits
+static bool crc_use_block_kernel(int B, int A) { return A >= 1024 && (long long)B * 128 < 148LL * 2048 * 4 || A >= 65536; }
+
 extern "C" int nrldpc_crc_encode(const int8_t *d_in, int B, int A, int poly_id, int8_t *d_out, void *stream)
 {
     int L; uint32_t poly;
     if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
     if (B < 0 || A < 0 || !d_in || !d_out) { set_error("crc_encode: bad argument"); return NRLDPC_EINVAL; }
     if (B == 0) return NRLDPC_OK;
-    crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 0, d_out, nullptr);
+    if (crc_use_block_kernel(B, A)) crc_block_kernel<<<B, kCrcBlockThreads, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 0, d_out, nullptr);
+    else crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 0, d_out, nullptr);
     NRLDPC_CUDA(cudaGetLastError());
     return L;
 }
@@ -218,7 +285,8 @@ extern "C" int nrldpc_crc_check(const int8_t *d_in, int B, int A, int poly_id, u
     if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
     if (B < 0 || A < 0 || !d_in || !d_err) { set_error("crc_check: bad argument"); return NRLDPC_EINVAL; }
     if (B == 0) return NRLDPC_OK;
-    crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 1, nullptr, d_err);
+    if (crc_use_block_kernel(B, A)) crc_block_kernel<<<B, kCrcBlockThreads, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 1, nullptr, d_err);
+    else crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 1, nullptr, d_err);
     NRLDPC_CUDA(cudaGetLastError());
     return L;
 }

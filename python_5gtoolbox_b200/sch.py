@@ -73,7 +73,10 @@ def sch_decode(LLr, G, TBSize, Qm, coderateby1024, num_of_layers, rv, Ncb_of, LD
     cur = np.asarray(current_LLr_dns)
     if HARQ_on and cur.size != 0:
         llr_dn = engine.harq_combine(llr_dn, torch.from_numpy(np.ascontiguousarray(cur, np.float64)).to(dev))
-    new_LLr_dns = llr_dn.cpu().numpy()
+    # the [C,N] float64 soft buffer goes back to the caller (HARQ state): copy it through pinned memory while
+    # the decoder runs
+    new_host = torch.empty(llr_dn.shape, dtype=torch.float64, pin_memory=True)
+    new_host.copy_(llr_dn, non_blocking=True)
     cfg = LDPC_decoder_config
     algo = cfg["algo"]
     if algo == 'min-sum':
@@ -81,13 +84,25 @@ def sch_decode(LLr, G, TBSize, Qm, coderateby1024, num_of_layers, rv, Ncb_of, LD
         ck = res["ck"][:, :K_apo].contiguous()
         if C > 1:
             engine.crc_check_device(ck, '24B')   # computed and ignored, like the reference (nr_dlsch_decode.py:93-98)
-        blocks = ck[:, :cbz].cpu().numpy()
+        # transport block = the codeblocks' payloads back to back (C * cbz == B); TB CRC on the device
+        tb = ck[:, :cbz].reshape(1, C * cbz).contiguous()
+        tb_err = engine.crc_check_device(tb, tb_crc_poly(A))
+        tbblk = tb[0, :A].cpu().numpy()
+        ok = int(tb_err.cpu()[0]) == 0   # synchronises: the pinned copy of the soft buffer is complete too
+        torch.cuda.synchronize()
+        return ok, tbblk, new_host.numpy()
     elif algo == 'BF':
+        torch.cuda.synchronize()
+        new_LLr_dns = new_host.numpy()
         ck, _, _ = engine.decode_bf_batch(new_LLr_dns, Zc, bgn, cfg["L"])
         blocks = ck[:, :cbz].astype(np.float64)
     else:
+        torch.cuda.synchronize()
+        new_LLr_dns = new_host.numpy()
         ck, _, _ = engine.decode_ref_batch(new_LLr_dns, Zc, bgn, cfg["L"], algo, cfg["alpha"], cfg["beta"], True, f64=True)
         blocks = ck[:, :cbz]
+    torch.cuda.synchronize()
+    new_LLr_dns = new_host.numpy()
     tbblkandcrc = np.zeros(B)
     tbblkandcrc[:C * cbz] = blocks.reshape(-1)
     tbblk, tbcrc_error = crc.nr_crc_decode(tbblkandcrc, tb_crc_poly(A))

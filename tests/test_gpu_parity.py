@@ -371,6 +371,24 @@ def test_crc_golden(eng):
     assert crc.nr_crc_decode(enc, "16", 12345)[1] == 0 and crc.nr_crc_decode(enc, "16", 0)[1] == 1
 
 
+def test_crc_long_blocks_vs_oracle(eng, oracle):
+    """Transport-block sized CRCs take the chunk-parallel kernel (one CTA per block, GF(2) linearity):
+    bit-exact against the oracle's bit-serial division, single blocks and batches."""
+    from python_5gtoolbox_b200 import crc
+    rng = np.random.default_rng(24)
+    for poly, n, B in [("24A", 966896, 1), ("24B", 8408, 115), ("16", 3824, 3), ("24A", 1024, 2), ("24C", 4097, 5),
+                       ("11", 65536, 2), ("6", 70001, 1), ("24A", 25 * 1000 + 7, 1)]:
+        blk = rng.integers(0, 2, (B, n)).astype("i1")
+        out = crc.nr_crc_encode_batch(blk, poly)
+        for b in range(B):
+            assert np.array_equal(out[b], oracle.nr_crc_encode(blk[b], poly)), (poly, n, b)
+        assert crc.nr_crc_decode(out[0], poly)[1] == 0
+        for pos in (0, n // 2, n - 1, n + 3):
+            bad = out[0].copy()
+            bad[pos] ^= 1
+            assert crc.nr_crc_decode(bad, poly)[1] == 1, (poly, n, pos)
+
+
 # ------------------------------------------------------------------ drop-in modules
 
 def test_dropin_modules_match_oracle(eng, oracle):
