@@ -48,13 +48,7 @@ static const QcCfg *get_cfg(int bgn, int Zc)
     return c;
 }
 
-// RAII device buffer for the synchronous host entry points
-struct DevBuf {
-    void *p = nullptr;
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
-    ~DevBuf() { if (p) cudaFree(p); }
-    template <typename T> T *as() { return static_cast<T *>(p); }
-};
+using DevBuf = ScratchBuf;
 
 // CSR -> CSC (edges of every column in ascending row order = the reference's B lists,
 // py5gphy/ldpc/nr_ldpc_decode.py:88-91)

@@ -58,6 +58,31 @@ int cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
+// Temporary device buffer of the synchronous host-buffer entry points: stream-ordered allocation from the
+// device's default memory pool (kept warm: release threshold = never), so a per-codeblock call of an unchanged
+// reference script does not pay a cudaMalloc / cudaFree pair per buffer.
+struct ScratchBuf {
+    void *p = nullptr;
+    cudaError_t alloc(size_t n)
+    {
+        static thread_local int warmed_dev = -1;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (warmed_dev != dev) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            warmed_dev = dev;
+        }
+        return cudaMallocAsync(&p, n ? n : 1, (cudaStream_t)0);
+    }
+    ~ScratchBuf() { if (p) cudaFreeAsync(p, (cudaStream_t)0); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
 // kernel launchers (device pointers)
 int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s);
 int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_iter, float alpha, float beta,

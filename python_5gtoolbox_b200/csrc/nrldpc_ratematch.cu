@@ -169,11 +169,7 @@ int check_rm_args(const char *what, int B, int N, int Ncb, int k0, int Qm)
     return NRLDPC_OK;
 }
 
-struct DevMem {
-    void *p = nullptr;
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
-    ~DevMem() { if (p) cudaFree(p); }
-};
+using DevMem = ScratchBuf;
 
 // offsets of the concatenated per-codeblock sequences (code block concatenation, 38.212 5.5)
 int host_offsets(const char *what, const int32_t *E, int B, int Qm, std::vector<long long> *off, long long *total)

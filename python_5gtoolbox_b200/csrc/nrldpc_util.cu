@@ -292,10 +292,7 @@ extern "C" int nrldpc_crc_check(const int8_t *d_in, int B, int A, int poly_id, u
 }
 
 namespace {
-struct TmpBuf {
-    void *p = nullptr;
-    ~TmpBuf() { if (p) cudaFree(p); }
-};
+using TmpBuf = ScratchBuf;
 }
 
 extern "C" int nrldpc_crc_encode_host(const int8_t *in, int B, int A, int poly_id, int8_t *out)
@@ -304,8 +301,8 @@ extern "C" int nrldpc_crc_encode_host(const int8_t *in, int B, int A, int poly_i
     if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
     if (B <= 0 || A < 0) return B == 0 ? L : NRLDPC_EINVAL;
     TmpBuf di, dout;
-    NRLDPC_CUDA(cudaMalloc(&di.p, (size_t)B * A + 1));
-    NRLDPC_CUDA(cudaMalloc(&dout.p, (size_t)B * (A + L)));
+    NRLDPC_CUDA(di.alloc((size_t)B * A + 1));
+    NRLDPC_CUDA(dout.alloc((size_t)B * (A + L)));
     NRLDPC_CUDA(cudaMemcpy(di.p, in, (size_t)B * A, cudaMemcpyHostToDevice));
     int rc = nrldpc_crc_encode((const int8_t *)di.p, B, A, poly_id, (int8_t *)dout.p, nullptr);
     if (rc < 0) return rc;
@@ -319,8 +316,8 @@ extern "C" int nrldpc_crc_check_host(const int8_t *in, int B, int A, int poly_id
     if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
     if (B <= 0 || A < 0) return B == 0 ? L : NRLDPC_EINVAL;
     TmpBuf di, de;
-    NRLDPC_CUDA(cudaMalloc(&di.p, (size_t)B * (A + L)));
-    NRLDPC_CUDA(cudaMalloc(&de.p, (size_t)B));
+    NRLDPC_CUDA(di.alloc((size_t)B * (A + L)));
+    NRLDPC_CUDA(de.alloc((size_t)B));
     NRLDPC_CUDA(cudaMemcpy(di.p, in, (size_t)B * (A + L), cudaMemcpyHostToDevice));
     int rc = nrldpc_crc_check((const int8_t *)di.p, B, A, poly_id, (uint8_t *)de.p, nullptr);
     if (rc < 0) return rc;
