@@ -200,3 +200,72 @@ def run_ldpc_simulation(Zc, bgn, crcpoly, algo_list, alpha_list, beta_list, mixe
         with open(filename, 'wb') as handle:
             pickle.dump([sim_config, test_config_list, test_results_list], handle, protocol=pickle.HIGHEST_PROTOCOL)
     return sim_config, test_config_list, test_results_list
+
+
+# ------------------------------------------------------------------ fixed-count BLER / BER curves (BASELINE config #5)
+
+def shard_range(n, rank, world):
+    """Contiguous share [lo, hi) of n codeblocks for `rank` of `world` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _device_point_counters(device, Zc, bgn, snr_db, crcpoly, L, alpha, beta, lo, hi, seed, early_term=True, chunk=16384):
+    """{codeblocks, block errors, bit errors, iterations} of codeblocks lo..hi-1 of one SNR point, generated
+    (Philox, codeblock id = its index), encoded, decoded and counted on the device."""
+    import ctypes
+    import torch
+    from . import engine, _lib
+    K = (22 if bgn == 1 else 10) * Zc
+    crc_len = 24 if crcpoly in ['24A', '24B'] else 16
+    A = K - crc_len
+    poly = {"24A": 3, "24B": 4, "16": 2}[crcpoly]
+    counters = torch.zeros(4, dtype=torch.int64, device=device)
+    L_ = _lib.lib()
+    with torch.cuda.device(device):
+        for i0 in range(lo, hi, chunk):
+            mm = min(chunk, hi - i0)
+            s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            bits = torch.empty((mm, A), dtype=torch.int8, device=device)
+            _lib.check(L_.nrldpc_random_bits_rows(bits.data_ptr(), mm, A, seed, i0, 1, s), "random_bits")
+            blk = torch.empty((mm, K), dtype=torch.int8, device=device)
+            _lib.check(L_.nrldpc_crc_encode(bits.data_ptr(), mm, A, poly, blk.data_ptr(), s), "crc")
+            dn = engine.encode_batch(blk.clone(), bgn, Zc)
+            llr = torch.empty(dn.shape, dtype=torch.float32, device=device)
+            _lib.check(L_.nrldpc_awgn_llr_rows(dn.data_ptr(), mm, dn.shape[1], float(snr_db), seed, i0, 1, llr.data_ptr(), s), "awgn")
+            r = engine.decode_batch(llr, Zc, bgn, L, alpha, beta, early_term)
+            engine.count_errors(blk, r["ck"], K, r["iters"], counters)
+    return counters
+
+
+def bler_curve(Zc, bgn, snr_db_list, n_per_point, L, alpha=1.0, beta=0.0, crcpoly='24A', *, seed=0x5601, device=None,
+               point_counters=None):
+    """BLER / BER / mean iterations of the min-sum decoder at every SNR of `snr_db_list` with a FIXED number of
+    codeblocks per point (10^6 in BASELINE config #5), device-generated inputs.
+
+    Sharding: rank k of W takes a contiguous share of every point's codeblocks (a codeblock's
+    bits and noise depend only on (seed, point, index), so any W sees the same codeblocks); the ONLY collective
+    is one all-reduce(SUM) of int64[n_points x 4] = {codeblocks, block errors, bit errors, iterations} at the
+    end.  Returns a list of dicts, one per SNR point.  `point_counters` replaces the device worker (tests)."""
+    d = _Dist()
+    if point_counters is None:
+        import torch
+        dev = torch.device(device if device is not None else "cuda")
+        def point_counters(p, snr_db, lo, hi):
+            return _device_point_counters(dev, Zc, bgn, snr_db, crcpoly, L, alpha, beta, lo, hi, seed + 7919 * p).tolist()
+        reduce_device = dev
+    else:
+        reduce_device = None
+    rows = []
+    for p, snr_db in enumerate(snr_db_list):
+        lo, hi = shard_range(n_per_point, d.rank, d.world)
+        rows.extend(int(v) for v in (point_counters(p, snr_db, lo, hi) if hi > lo else [0, 0, 0, 0]))
+    total = d.sum(rows, reduce_device)
+    K = (22 if bgn == 1 else 10) * Zc
+    out = []
+    for p, snr_db in enumerate(snr_db_list):
+        n, be, bit, it = total[4 * p:4 * p + 4]
+        out.append({"snr_db": snr_db, "codeblocks": n, "block_errors": be, "bit_errors": bit, "bler": be / max(n, 1),
+                    "ber": bit / max(n * K, 1), "mean_iters": it / max(n, 1)})
+    return out

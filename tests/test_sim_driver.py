@@ -122,6 +122,48 @@ def test_gpu_driver_device_rng_bler_in_ci():
     assert table[0][1] < 0.012
 
 
+def test_bler_curve_sharding_single_reduce():
+    """bler_curve: contiguous shares cover every codeblock once for any world size, and the counters of a
+    sharded run (emulated ranks, summed like the all-reduce does) equal the single-rank ones."""
+    from python_5gtoolbox_b200 import sim
+    for n in (0, 1, 7, 1000, 10 ** 6 + 3):
+        for world in (1, 2, 3, 8):
+            spans = [sim.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+    def fake(p, snr_db, lo, hi):   # per-codeblock deterministic "results": a function of (point, index) only
+        idx = np.arange(lo, hi)
+        be = ((idx * 2654435761 + p) % 17 == 0)
+        return [hi - lo, int(be.sum()), int((be * (idx % 5 + 1)).sum()), int((idx % 9 + 1).sum())]
+
+    one = sim.bler_curve(12, 1, [0.0, 1.0], 5000, 10, point_counters=fake)
+    parts = []
+    for r in range(4):
+        lo, hi = sim.shard_range(5000, r, 4)
+        parts.append([fake(p, s, lo, hi) for p, s in enumerate([0.0, 1.0])])
+    summed = np.sum(np.array(parts), axis=0)
+    for p in range(2):
+        assert [one[p]["codeblocks"], one[p]["block_errors"], one[p]["bit_errors"]] == summed[p][:3].tolist()
+        assert one[p]["bler"] == summed[p][1] / 5000 and abs(one[p]["mean_iters"] - summed[p][3] / 5000) < 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_bler_curve_fixed_count():
+    """Device BLER curve, fixed count per point: monotone in SNR, consistent counters, reproducible (same
+    seed -> identical counters, whatever the chunking of the work)."""
+    from python_5gtoolbox_b200 import sim
+    a = sim.bler_curve(28, 1, [-1.0, 0.0, 1.0], 6000, 16, 0.8, 0.3)
+    b = sim.bler_curve(28, 1, [-1.0, 0.0, 1.0], 6000, 16, 0.8, 0.3)
+    assert a == b
+    assert all(r["codeblocks"] == 6000 for r in a)
+    assert a[0]["bler"] > a[1]["bler"] >= a[2]["bler"] and a[0]["bler"] > 0.05 and a[2]["bler"] < 0.01
+    assert all(r["bit_errors"] >= r["block_errors"] for r in a) and a[0]["mean_iters"] > a[2]["mean_iters"]
+    # shipped value: mixed (0.8,0.3) L=32 Zc=28 BG1 at -1 dB: 0.095 (out/mixed_MS_search_pair_ZC28, BASELINE.md)
+    c = sim.bler_curve(28, 1, [-1.0], 4000, 32, 0.8, 0.3)
+    assert abs(c[0]["bler"] - 0.095) < 4 * (0.095 * 0.905 / 400 + 0.095 * 0.905 / 4000) ** 0.5 + 0.005
+
+
 # BLER values of the reference's shipped tables (out/NMS_search_alpha_*, out/OMS_search_beta_*, BASELINE.md 3):
 # (Zc, bgn, algo, parameter, L, snr_db, shipped BLER).  The reference's trial count per point is not stored
 # (granularity suggests 400-2000): the check uses n_ref = 400 for its binomial interval.
