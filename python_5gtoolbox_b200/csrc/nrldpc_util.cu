@@ -35,12 +35,23 @@ __global__ void random_bits_kernel(int8_t *bits, long long rows, long long cols,
                                    unsigned long long ctr0, long long first_id, long long id_stride)
 {
     const long long bpr = (cols + 127) / 128, nblk = rows * bpr;  // one Philox block = 128 bits
+    const bool vec8 = (cols % 8 == 0) && (reinterpret_cast<uintptr_t>(bits) % 8 == 0);
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nblk; t += (long long)gridDim.x * blockDim.x) {
         const long long row = t / bpr, blk = t - row * bpr;
         const uint4 x = philox_at(seed, ctr0 + (unsigned long long)((first_id + row * id_stride) * bpr + blk));
         const uint32_t w[4] = {x.x, x.y, x.z, x.w};
         const long long base = blk * 128;
         int8_t *out = bits + row * cols;
+        if (vec8 && base + 128 <= cols) {
+            // 8 bits -> 8 bytes per store: nibble * 0x00204081 & 0x01010101 spreads 4 bits over 4 bytes
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t byte = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                const uint32_t lo = ((byte & 0xfu) * 0x00204081u) & 0x01010101u, hi = ((byte >> 4) * 0x00204081u) & 0x01010101u;
+                *reinterpret_cast<uint2 *>(out + base + 8 * i) = make_uint2(lo, hi);
+            }
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < 128; ++i)
             if (base + i < cols) out[base + i] = (int8_t)((w[i >> 5] >> (i & 31)) & 1u);
@@ -52,18 +63,30 @@ __global__ void awgn_llr_kernel(const int8_t *__restrict__ dn, long long rows, l
                                 float *__restrict__ llr)
 {
     const long long bpr = (cols + 3) / 4, nblk = rows * bpr;  // one Philox block = 4 normals
+    const bool vec4 = (cols % 4 == 0) && (reinterpret_cast<uintptr_t>(dn) % 4 == 0) && (reinterpret_cast<uintptr_t>(llr) % 16 == 0);
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nblk; t += (long long)gridDim.x * blockDim.x) {
         const long long row = t / bpr, blk = t - row * bpr;
         const uint4 x = philox_at(seed ^ 0x9E3779B97F4A7C15ull, ctr0 + (unsigned long long)((first_id + row * id_stride) * bpr + blk));
         // Box-Muller on two uniform pairs
         const float u0 = ((x.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((x.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
         const float u2 = ((x.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((x.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+        // (SFU logarithm: relative error ~2^-21 on the radius, far below the Monte-Carlo resolution of a BLER point)
+        const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
         float s0, c0, s1, c1;
         sincospif(2.0f * u1, &s0, &c0);
         sincospif(2.0f * u3, &s1, &c1);
         const float n[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
         const long long base = blk * 4;
+        if (vec4 && base + 4 <= cols) {
+            const char4 d4 = *reinterpret_cast<const char4 *>(dn + row * cols + base);
+            const int d[4] = {d4.x, d4.y, d4.z, d4.w};
+            float4 o;
+            float *op = &o.x;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = d[i] < 0 ? 0.0f : scale * ((1.0f - 2.0f * (float)d[i]) + sigma * n[i]);
+            *reinterpret_cast<float4 *>(llr + row * cols + base) = o;
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (base + i < cols) {
@@ -132,7 +155,7 @@ __global__ void crc_kernel(const int8_t *__restrict__ in, int B, int A, int L, u
 // (s_t = message bits after chunk t), so  M(x) x^L mod P = sum_t (r_t * x^{s_t}) mod P  with r_t the CRC of
 // chunk t alone.  Each thread runs the bit-serial register over its own chunk, multiplies by x^{s_t} mod P
 // (square-and-multiply in GF(2)[x]/P, ~40 L-step products) and the partial remainders are XOR-reduced.
-constexpr int kCrcBlockThreads = 256;
+constexpr int kCrcBlockThreads = 256;  // long blocks; medium blocks (a codeblock's payload) use 64: fewer x^s products
 
 __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b, int L, uint32_t poly, uint32_t mask)
 {
@@ -146,10 +169,12 @@ __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b, int L, ui
     return res;
 }
 
-__global__ void __launch_bounds__(kCrcBlockThreads)
+template <int T>
+__global__ void __launch_bounds__(T)
 crc_block_kernel(const int8_t *__restrict__ in, int A, int L, uint32_t poly, int mode, int8_t *__restrict__ out,
                  uint8_t *__restrict__ err)
 {
+    constexpr int kCrcBlockThreads = T;
     __shared__ uint32_t s_part[kCrcBlockThreads / 32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int len_in = mode ? A + L : A;
@@ -264,8 +289,9 @@ static int crc_poly(int poly_id, int *L, uint32_t *poly)
     return NRLDPC_OK;
 }
 
-// long blocks, or too few blocks to fill the GPU with one thread each: one CTA per block of bits
-static bool crc_use_block_kernel(int B, int A) { return A >= 1024 && (long long)B * 128 < 148LL * 2048 * 4 || A >= 65536; }
+// long blocks: one CTA per block of bits
+// (one thread per block walks its bits serially with uncoalesced byte loads: only good for short blocks)
+static bool crc_use_block_kernel(int B, int A) { (void)B; return A >= 1024; }
 
 extern "C" int nrldpc_crc_encode(const int8_t *d_in, int B, int A, int poly_id, int8_t *d_out, void *stream)
 {
@@ -273,7 +299,10 @@ extern "C" int nrldpc_crc_encode(const int8_t *d_in, int B, int A, int poly_id, 
     if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
     if (B < 0 || A < 0 || !d_in || !d_out) { set_error("crc_encode: bad argument"); return NRLDPC_EINVAL; }
     if (B == 0) return NRLDPC_OK;
-    if (crc_use_block_kernel(B, A)) crc_block_kernel<<<B, kCrcBlockThreads, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 0, d_out, nullptr);
+    if (crc_use_block_kernel(B, A)) {
+        if (A >= 32768) crc_block_kernel<kCrcBlockThreads><<<B, kCrcBlockThreads, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 0, d_out, nullptr);
+        else crc_block_kernel<64><<<B, 64, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 0, d_out, nullptr);
+    }
     else crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 0, d_out, nullptr);
     NRLDPC_CUDA(cudaGetLastError());
     return L;
@@ -285,7 +314,10 @@ extern "C" int nrldpc_crc_check(const int8_t *d_in, int B, int A, int poly_id, u
     if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
     if (B < 0 || A < 0 || !d_in || !d_err) { set_error("crc_check: bad argument"); return NRLDPC_EINVAL; }
     if (B == 0) return NRLDPC_OK;
-    if (crc_use_block_kernel(B, A)) crc_block_kernel<<<B, kCrcBlockThreads, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 1, nullptr, d_err);
+    if (crc_use_block_kernel(B, A)) {
+        if (A >= 32768) crc_block_kernel<kCrcBlockThreads><<<B, kCrcBlockThreads, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 1, nullptr, d_err);
+        else crc_block_kernel<64><<<B, 64, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 1, nullptr, d_err);
+    }
     else crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 1, nullptr, d_err);
     NRLDPC_CUDA(cudaGetLastError());
     return L;
