@@ -49,6 +49,28 @@ constexpr int kMaxS = 16;  // warp groups per r-tile
 #ifndef NRLDPC_SIGN_FMA
 #define NRLDPC_SIGN_FMA 0
 #endif
+#ifndef NRLDPC_MASKREG
+#define NRLDPC_MASKREG 1     // argmin-field test as ONE LOP3 with predicate output: ((bits ^ k) & mask register) != 0
+#endif
+#ifndef NRLDPC_FIRST_IT
+#define NRLDPC_FIRST_IT 1    // first check pass without record decode (all records are zero: Lq = LQ): 1 = kernels without
+                             // early termination only (with it, the extra code costs more than it saves: measured), 2 = all
+#endif
+#ifndef NRLDPC_MIRROR_LOOP
+#define NRLDPC_MIRROR_LOOP 0   // 1: the mirror stores of a check row sit in a one-trip loop (trip count opaque to ptxas), which
+#endif                         // keeps them behind a real warp-uniform branch instead of predicated off in every warp
+#ifndef NRLDPC_TILE_ROT
+#define NRLDPC_TILE_ROT 0      // 1: group g's tiles rotated by g, so the tile-0 warps of the groups sit on different schedulers
+#endif
+#ifndef NRLDPC_COLD_FMA_MAXDEG
+#define NRLDPC_COLD_FMA_MAXDEG 99  // rows of a larger degree find the argmin with FADD + SHF + FLO (ALU pipe) instead of 3 FMA-pipe ops
+#endif
+#ifndef NRLDPC_GROUP_SYNC_CN
+#define NRLDPC_GROUP_SYNC_CN 0  // > 0: named barrier among the warps of a group every this many check rows (bounds their drift
+#endif                          // in the straight-line code, which is streamed from L2: the instruction caches hold 6 KB / 32 KB)
+#ifndef NRLDPC_GROUP_SYNC_VN
+#define NRLDPC_GROUP_SYNC_VN 0  // same, every this many columns of the variable pass
+#endif
 #ifndef NRLDPC_PF_SUM
 #define NRLDPC_PF_SUM 16  // prefetch the next check row's inputs when deg(current) + deg(next) <= this (registers)
 #endif
@@ -173,7 +195,20 @@ template <class C> struct Th {  // per-thread constants
     char *p4, *p4m2;            // smem + r4, smem + r4m2
     int r, tile;
     int w4[C::tiles + 1];       // warp-uniform wrap offsets in bytes of a 4-byte-stride array: w4[t] = tile >= t ? -4 Zc : 0
+    uint32_t mk[3];             // argmin-field masks of the three word kinds, held in (opaque) registers
+    int one;                    // 1, opaque to ptxas
 };
+
+// Is edge K the argmin edge of the row whose sign/argmin word is `bits`?  With the mask in a register the
+// test is one LOP3 with a predicate output, (bits ^ K<<s) & mask != 0, instead of LOP3 + ISETP.
+template <class C, int I, int K> __device__ __forceinline__ bool is_argmin(const Th<C> &th, uint32_t bits)
+{
+#if NRLDPC_MASKREG
+    return ((bits ^ ((uint32_t)K << C::idx_shift(I))) & th.mk[C::kind(I)]) == 0;
+#else
+    return ((bits ^ ((uint32_t)K << C::idx_shift(I))) & C::idx_mask(I)) == 0;
+#endif
+}
 
 // sign/argmin word access
 template <class C, int I> __device__ __forceinline__ uint32_t load_bits(const char *p)
@@ -219,28 +254,41 @@ template <class C> __device__ __forceinline__ Th<C> opaque(Th<C> th)
     return th;
 }
 
-template <class C, int I> __device__ __forceinline__ RowIn<C, I> load_row(const Th<C> &th_)
+// FIRST: the first check pass of a codeblock -- every record is zero (Lr = 0, :101), so nothing is read of it.
+template <class C, int I, bool FIRST = false> __device__ __forceinline__ RowIn<C, I> load_row(const Th<C> &th_)
 {
     const Th<C> th = opaque(th_);
     RowIn<C, I> in;
-    in.m.x = *reinterpret_cast<const float *>(th.smem + C::mags_base(I) + th.r4);
-    in.m.y = *reinterpret_cast<const float *>(th.smem + (C::mags_base(I) + C::mag2_dist) + th.r4);
-    in.bits = load_bits<C, I>(th.smem + C::bits_base(I) + th.r4);
+    if constexpr (FIRST) {
+        in.m = make_float2(0.f, 0.f);
+        in.bits = 0;
+    } else {
+        in.m.x = *reinterpret_cast<const float *>(th.smem + C::mags_base(I) + th.r4);
+        in.m.y = *reinterpret_cast<const float *>(th.smem + (C::mags_base(I) + C::mag2_dist) + th.r4);
+        in.bits = load_bits<C, I>(th.smem + C::bits_base(I) + th.r4);
+    }
     load_row_x<C, I>(in, th, std::make_integer_sequence<int, RowIn<C, I>::NC>{});
     return in;
 }
 
-template <class C, int I, int K, bool ET>
+template <class C, int I, int K, bool ET, bool FIRST>
 __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, float &m2, uint32_t &synd, const Th<C> &th,
                                           const RowIn<C, I> &in, uint32_t idxf, float llr_e)
 {
     constexpr int DEG = C::deg(I);
     constexpr bool EXT = I >= 4;
-    const bool isidx = idxf == ((uint32_t)K << C::idx_shift(I));
-    const float lr = record_lr(in.m, isidx, in.bits << (31 - (DEG - 1 - K)));
+    float lr = 0.f;  // FIRST: Lr = +0 on every edge
+    if constexpr (!FIRST) {
+#if NRLDPC_MASKREG
+        const bool isidx = is_argmin<C, I, K>(th, in.bits);
+#else
+        const bool isidx = idxf == ((uint32_t)K << C::idx_shift(I));
+#endif
+        lr = record_lr(in.m, isidx, in.bits << (31 - (DEG - 1 - K)));
+    }
     float x;
     if constexpr (EXT && K == DEG - 1) {
-        x = __fadd_rn(llr_e, lr);  // posterior of the degree-1 extension variable (:126)
+        x = __fadd_rn(llr_e, lr);  // posterior of the degree-1 extension variable (:126); -0.0 + 0 = +0.0
         if constexpr (ET) {
             const uint32_t hb = __ballot_sync(0xffffffffu, x < 0.f);
             if ((th.r & 31) == 0) reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + th.tile] = hb;
@@ -249,7 +297,7 @@ __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, floa
         x = in.x[K];
     }
     if constexpr (ET) synd ^= __float_as_uint(x);  // sign bit = hard decision LQ<0 (:107-108)
-    q[K] = __fsub_rn(x, lr);                        // Lq = LQ - Lr (:131)
+    q[K] = FIRST ? x : __fsub_rn(x, lr);            // Lq = LQ - Lr (:131); LQ is never -0.0, so LQ - 0 == LQ bit for bit
     // |m1| = first minimum, sign of m1 = running sign product, m2 = second minimum (the first two edges
     // spelled out: no arithmetic against the +inf start values)
     if constexpr (K == 0) {
@@ -263,18 +311,18 @@ __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, floa
     }
 }
 
-template <class C, int I, bool ET, int... K>
+template <class C, int I, bool ET, bool FIRST, int... K>
 __device__ __forceinline__ void cn_edges_s(float (&q)[C::deg(I)], float &m1, float &m2, uint32_t &synd, const Th<C> &th,
                                            const RowIn<C, I> &in, uint32_t idxf, float llr_e,
                                            std::integer_sequence<int, K...>)
 {
-    (cn_edge_s<C, I, K, ET>(q, m1, m2, synd, th, in, idxf, llr_e), ...);
+    (cn_edge_s<C, I, K, ET, FIRST>(q, m1, m2, synd, th, in, idxf, llr_e), ...);
 }
 
 // One check row of row-block I (compile time), lifted index r: syndrome bit of the current hard
 // decisions, then the min-sum update of its record from Lq = LQ - Lr_old
 // (py5gphy/ldpc/nr_ldpc_decode.py:107-123, :178-227).
-template <class C, int I, bool ET, bool B0>
+template <class C, int I, bool ET, bool B0, bool FIRST = false>
 __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int *flag, const RowIn<C, I> &in,
                                          const float llr_e)
 {
@@ -285,7 +333,7 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
     float q[DEG];
     float m1 = __uint_as_float(kInfBits), m2 = m1;
     uint32_t synd = 0;
-    cn_edges_s<C, I, ET>(q, m1, m2, synd, th, in, idxf, llr_e, std::make_integer_sequence<int, DEG>{});
+    cn_edges_s<C, I, ET, FIRST>(q, m1, m2, synd, th, in, idxf, llr_e, std::make_integer_sequence<int, DEG>{});
     // signs of Lq and the argmin: an edge is "hot" when |Lq| == min1, i.e. min1 - |Lq| is +0 (never NaN
     // for finite inputs).  Edges that tie at min1 make min2 == min1, so any hot edge may carry the index.
     constexpr uint32_t ALL = (1u << DEG) - 1u;
@@ -309,6 +357,8 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
     // "cold" when it is negative.  Edges that tie at min1 make min2 == min1, so then ANY index gives the
     // same messages.
 #if NRLDPC_COLD_FMA
+    uint32_t kmin;
+    if constexpr (DEG <= NRLDPC_COLD_FMA_MAXDEG) {
     // position of the hot edge = sum(all k) - sum(cold k), with cold = sat(d * -inf) in {0, 1} exactly and the
     // sum kept as an exact small integer on top of 2^23, whose low mantissa bits are then the position
     float hotpos = 8388608.0f + (float)(DEG * (DEG - 1) / 2);
@@ -317,7 +367,13 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
         const float c = __saturatef(__fmul_rn(__fsub_rn(fabsf(m1), fabsf(q[k])), __uint_as_float(0xff800000u)));
         hotpos = __fmaf_rn(c, -(float)k, hotpos);
     }
-    const uint32_t kmin = __float_as_uint(hotpos);  // low bits; masked to the index field below
+    kmin = __float_as_uint(hotpos);  // low bits; masked to the index field below
+    } else {
+        uint32_t cold = 0;
+#pragma unroll
+        for (int k = 0; k < DEG; ++k) cold = push_top_bit(cold, __float_as_uint(__fsub_rn(fabsf(m1), fabsf(q[k]))));
+        kmin = (uint32_t)(DEG - 32) + (uint32_t)__clz(~cold & ALL);  // DEG-1 - (31 - clz): smallest hot k
+    }
 #else
     uint32_t cold = 0;
 #pragma unroll
@@ -335,6 +391,19 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
     *reinterpret_cast<float *>(rec + C::mag2_dist) = mag2;
     store_bits<C, I>(bp, nb);
     if (th.tile == 0) {  // mirror of the first 32 records behind the array (rotated reads of the variable pass)
+#if NRLDPC_MIRROR_LOOP
+        int n = th.one;
+#pragma unroll 1
+        do {  // (volatile: loop-invariant stores would be sunk out of the loop and the loop deleted)
+            *reinterpret_cast<volatile float *>(rec + C::ZC * 4) = mag1;
+            *reinterpret_cast<volatile float *>(rec + C::mag2_dist + C::ZC * 4) = mag2;
+            if constexpr (C::kind(I) == 2) *reinterpret_cast<volatile uint32_t *>(bp + C::ZC * 4) = nb;
+            else if constexpr (C::kind(I) == 1) *reinterpret_cast<volatile uint16_t *>(bp + C::ZC * 4) = (uint16_t)nb;
+            else *reinterpret_cast<volatile uint8_t *>(bp + C::ZC * 4) = (uint8_t)nb;
+        } while (--n > 0);
+    }
+    if (false) {
+#endif
         *reinterpret_cast<float *>(rec + C::ZC * 4) = mag1;
         *reinterpret_cast<float *>(rec + C::mag2_dist + C::ZC * 4) = mag2;
         store_bits<C, I>(bp + C::ZC * 4, nb);
@@ -357,25 +426,34 @@ template <class C, int I, bool ET> __device__ __forceinline__ float load_ext_llr
 // above the previous row's record stores (it cannot prove they do not alias), so the next row's inputs
 // are loaded, in program order, BEFORE the current row is computed and stored; its channel LLR (L2) too.
 // Rows whose combined degree exceeds NRLDPC_PF_SUM load their inputs after the store instead (registers).
-template <class C, bool ET, bool B0, int SUB, int O = 0>
+// named barrier (id 1 + SUB) among the warps of group SUB
+template <class C, int SUB> __device__ __forceinline__ void group_sync()
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(1 + SUB), "n"(C::tiles * 32) : "memory");
+}
+
+template <class C, bool ET, bool B0, bool FIRST, int SUB, int O = 0>
 __device__ __forceinline__ void cn_pass_s(const DecArgs &a, const Th<C> &th, int *flag,
                                           const RowIn<C, kRows<C>.item[SUB][O]> &in_cur, const float llr_cur)
 {
     constexpr int I = kRows<C>.item[SUB][O];
+#if NRLDPC_GROUP_SYNC_CN > 0
+    if constexpr (O > 0 && O % NRLDPC_GROUP_SYNC_CN == 0) group_sync<C, SUB>();
+#endif
     if constexpr (O + 1 < kRows<C>.n[SUB]) {
         constexpr int In = kRows<C>.item[SUB][O + 1];
         const float llr_nxt = load_ext_llr<C, In, ET>(th);
         if constexpr (C::deg(I) + C::deg(In) <= NRLDPC_PF_SUM) {
-            const RowIn<C, In> in_nxt = load_row<C, In>(th);
-            cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
-            cn_pass_s<C, ET, B0, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
+            const RowIn<C, In> in_nxt = load_row<C, In, FIRST>(th);
+            cn_row_s<C, I, ET, B0, FIRST>(a, th, flag, in_cur, llr_cur);
+            cn_pass_s<C, ET, B0, FIRST, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
         } else {
-            cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
-            const RowIn<C, In> in_nxt = load_row<C, In>(th);
-            cn_pass_s<C, ET, B0, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
+            cn_row_s<C, I, ET, B0, FIRST>(a, th, flag, in_cur, llr_cur);
+            const RowIn<C, In> in_nxt = load_row<C, In, FIRST>(th);
+            cn_pass_s<C, ET, B0, FIRST, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
         }
     } else {
-        cn_row_s<C, I, ET, B0>(a, th, flag, in_cur, llr_cur);
+        cn_row_s<C, I, ET, B0, FIRST>(a, th, flag, in_cur, llr_cur);
     }
 }
 
@@ -385,7 +463,7 @@ __device__ __forceinline__ void vn_entry_s(float &acc, const Th<C> &th)
     constexpr int e = C::cedge(J, Nn), i = C::row_of(e), k = e - C::G::rowptr(i), DEGI = C::deg(i);
     constexpr int back = (C::ZC - C::P(e)) % C::ZC, t = C::wrap_tile(back);  // check r = (c - P) mod Zc
     const uint32_t bits = load_bits<C, i>(th.smem + (C::bits_base(i) + 4 * back) + th.r4 + th.w4[t]);
-    const bool isidx = ((bits ^ ((uint32_t)k << C::idx_shift(i))) & C::idx_mask(i)) == 0;
+    const bool isidx = is_argmin<C, i, k>(th, bits);
     // only the magnitude this edge uses is read (one 128-byte wavefront): mag2 on the argmin edge, mag1 elsewhere
 #if NRLDPC_VN_PSEL
     const float mag = *reinterpret_cast<const float *>((isidx ? th.p4m2 : th.p4) + ((C::mags_base(i) + 4 * back) + th.w4[t]));
@@ -433,6 +511,9 @@ template <class C, int SUB, int O = 0>
 __device__ __forceinline__ void vn_pass_s(const Th<C> &th, const float lv_cur, const float lq_prev)
 {
     if constexpr (O < kCols<C>.n[SUB]) {
+#if NRLDPC_GROUP_SYNC_VN > 0
+        if constexpr (O > 0 && O % NRLDPC_GROUP_SYNC_VN == 0) group_sync<C, SUB>();
+#endif
         float lv_nxt = 0.f;
         if constexpr (O + 1 < kCols<C>.n[SUB]) lv_nxt = load_col_llr<C, kCols<C>.item[SUB][O + 1]>(th);
         const float lq = vn_col_s<C, kCols<C>.item[SUB][O]>(th, lv_cur);
@@ -481,12 +562,12 @@ __device__ __forceinline__ void final_pass_s(const Th<C> &th, int *flag)
 }
 
 // run PASS<SUB> for the warp's group (sub is warp-uniform)
-template <class C, bool ET, bool B0, int SUB = 0>
+template <class C, bool ET, bool B0, bool FIRST, int SUB = 0>
 __device__ __forceinline__ void run_cn(int sub, const DecArgs &a, const Th<C> &th, int *flag)
 {
     if constexpr (SUB < C::S) {
-        if (sub == SUB) cn_pass_s<C, ET, B0, SUB>(a, th, flag, load_row<C, kRows<C>.item[SUB][0]>(th), load_ext_llr<C, kRows<C>.item[SUB][0], ET>(th));
-        else run_cn<C, ET, B0, SUB + 1>(sub, a, th, flag);
+        if (sub == SUB) cn_pass_s<C, ET, B0, FIRST, SUB>(a, th, flag, load_row<C, kRows<C>.item[SUB][0], FIRST>(th), load_ext_llr<C, kRows<C>.item[SUB][0], ET>(th));
+        else run_cn<C, ET, B0, FIRST, SUB + 1>(sub, a, th, flag);
     }
 }
 template <class C, int SUB = 0>
@@ -543,6 +624,9 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     Th<C> th;
     th.smem = smem;
     th.tile = warp % C::tiles;
+#if NRLDPC_TILE_ROT
+    th.tile = (th.tile + sub) % C::tiles;
+#endif
 #endif
     th.r = min(th.tile * 32 + lane, ZC - 1);
     th.r4 = (uint32_t)th.r * 4u;
@@ -551,6 +635,11 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     th.p4m2 = smem + th.r4m2;
 #pragma unroll
     for (int t = 0; t <= C::tiles; ++t) th.w4[t] = (th.tile >= t) ? -4 * ZC : 0;
+    {   // masks ptxas cannot fold back into immediates: B > 0 in every launch, so `zero` is 0 -- at run time only
+        const uint32_t zero = (uint32_t)a.B >> 31;
+        th.mk[0] = 0xe0u + zero, th.mk[1] = 0xf000u + zero, th.mk[2] = 0x1f000000u + zero;
+        asm volatile("add.s32 %0, %1, 1;" : "=r"(th.one) : "r"(zero));  // 1, to neither nvvm nor ptxas
+    }
 
     // Persistent CTA (one per SM: the codeblock state fills shared memory): codeblocks blockIdx.x,
     // blockIdx.x + gridDim.x, ...  The channel LLRs are read straight from global memory every iteration
@@ -566,7 +655,9 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
         {
             constexpr int z0 = C::off_mags / 16, z1 = C::smem_bytes / 16;
             static_assert(C::off_mags % 16 == 0 && C::smem_bytes % 16 == 0, "16-byte zero fill");
-            for (int t = z0 + tid; t < z1; t += NT) reinterpret_cast<uint4 *>(smem)[t] = make_uint4(0, 0, 0, 0);
+            // (with the specialised first check pass every record is written before it is read, unless no pass runs)
+            if (!(NRLDPC_FIRST_IT > 1 || (NRLDPC_FIRST_IT && !ET)) || a.max_iter <= 0)
+                for (int t = z0 + tid; t < z1; t += NT) reinterpret_cast<uint4 *>(smem)[t] = make_uint4(0, 0, 0, 0);
             for (int t = tid; t < 2 * C::LQS; t += NT) reinterpret_cast<float *>(smem + C::lq_base(0))[t] = 0.f;
             if (tid < 2) s_flag[tid] = 0;
             for (int j = 2 + sub; j < C::ncore; j += C::S) {
@@ -583,7 +674,12 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
         for (; it < a.max_iter; ++it) {
             int *flag = &s_flag[it & 1];
 #ifndef NRLDPC_EXP_NO_CN
-            run_cn<C, ET, B0>(sub, a, th, flag);
+#if NRLDPC_FIRST_IT
+            if ((NRLDPC_FIRST_IT > 1 || !ET) && it == 0) run_cn<C, ET, B0, true>(sub, a, th, flag);
+            else run_cn<C, ET, B0, false>(sub, a, th, flag);
+#else
+            run_cn<C, ET, B0, false>(sub, a, th, flag);
+#endif
 #endif
             __syncthreads();
             if (ET) {

@@ -26,4 +26,5 @@ for i in range(n):
     ev1.record()
     torch.cuda.synchronize()
     print(f"launch {i}: {ev0.elapsed_time(ev1):.3f} ms, {B * 8448 / ev0.elapsed_time(ev1) / 1e6:.3f} Gbit/s, "
-          f"ok={float(r['status'].float().mean()):.3f} iters={float(r['iters'].float().mean()):.2f}")
+          f"ok={float(r['status'].float().mean()):.3f} iters={float(r['iters'].float().mean()):.2f} "
+          f"sum={int(r['info'].to(torch.int64).sum()) & 0xffffffffffff:x}")
