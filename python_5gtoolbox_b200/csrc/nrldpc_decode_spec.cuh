@@ -71,8 +71,14 @@ constexpr int kMaxS = 16;  // warp groups per r-tile
 #ifndef NRLDPC_GROUP_SYNC_VN
 #define NRLDPC_GROUP_SYNC_VN 0  // same, every this many columns of the variable pass
 #endif
+#ifndef NRLDPC_PF_LLR2
+#define NRLDPC_PF_LLR2 1  // channel LLR of a check row's extension variable fetched two rows ahead (L2 latency) instead of one
+#endif
+#ifndef NRLDPC_FINAL_PACKED
+#define NRLDPC_FINAL_PACKED 1  // final syndrome on bit-packed hard decisions (lifting sizes that are a multiple of 32)
+#endif
 #ifndef NRLDPC_PF_SUM
-#define NRLDPC_PF_SUM 16  // prefetch the next check row's inputs when deg(current) + deg(next) <= this (registers)
+#define NRLDPC_PF_SUM 20  // prefetch the next check row's inputs when deg(current) + deg(next) <= this (registers)
 #endif
 
 template <int BGN> struct Graph;
@@ -434,7 +440,8 @@ template <class C, int SUB> __device__ __forceinline__ void group_sync()
 
 template <class C, bool ET, bool B0, bool FIRST, int SUB, int O = 0>
 __device__ __forceinline__ void cn_pass_s(const DecArgs &a, const Th<C> &th, int *flag,
-                                          const RowIn<C, kRows<C>.item[SUB][O]> &in_cur, const float llr_cur)
+                                          const RowIn<C, kRows<C>.item[SUB][O]> &in_cur, const float llr_cur,
+                                          const float llr_nxt_in = 0.f)
 {
     constexpr int I = kRows<C>.item[SUB][O];
 #if NRLDPC_GROUP_SYNC_CN > 0
@@ -442,15 +449,21 @@ __device__ __forceinline__ void cn_pass_s(const DecArgs &a, const Th<C> &th, int
 #endif
     if constexpr (O + 1 < kRows<C>.n[SUB]) {
         constexpr int In = kRows<C>.item[SUB][O + 1];
-        const float llr_nxt = load_ext_llr<C, In, ET>(th);
+#if NRLDPC_PF_LLR2
+        const float llr_nxt = llr_nxt_in;
+        float llr_nn = 0.f;
+        if constexpr (O + 2 < kRows<C>.n[SUB]) llr_nn = load_ext_llr<C, kRows<C>.item[SUB][O + 2], ET>(th);
+#else
+        const float llr_nxt = load_ext_llr<C, In, ET>(th), llr_nn = 0.f;
+#endif
         if constexpr (C::deg(I) + C::deg(In) <= NRLDPC_PF_SUM) {
             const RowIn<C, In> in_nxt = load_row<C, In, FIRST>(th);
             cn_row_s<C, I, ET, B0, FIRST>(a, th, flag, in_cur, llr_cur);
-            cn_pass_s<C, ET, B0, FIRST, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
+            cn_pass_s<C, ET, B0, FIRST, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt, llr_nn);
         } else {
             cn_row_s<C, I, ET, B0, FIRST>(a, th, flag, in_cur, llr_cur);
             const RowIn<C, In> in_nxt = load_row<C, In, FIRST>(th);
-            cn_pass_s<C, ET, B0, FIRST, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt);
+            cn_pass_s<C, ET, B0, FIRST, SUB, O + 1>(a, th, flag, in_nxt, llr_nxt, llr_nn);
         }
     } else {
         cn_row_s<C, I, ET, B0, FIRST>(a, th, flag, in_cur, llr_cur);
@@ -530,12 +543,13 @@ __device__ __forceinline__ void final_edges_s(uint32_t &synd, const Th<C> &th, s
 {
     ((synd ^= (load_lq_rot<C, C::G::rowptr(I) + K>(th) <= 0.f) ? 1u : 0u), ...);
 }
-template <class C, int I>
-__device__ __forceinline__ void final_row_s(const Th<C> &th, int *flag)
+// CORE = false: only the hard bit of the extension variable (the packed final syndrome does the rest).
+template <class C, int I, bool CORE = true>
+__device__ __forceinline__ void final_row_s(const Th<C> &th, int *flag, const float llr_e)
 {
     constexpr int DEG = C::deg(I), NCORE = (I >= 4) ? DEG - 1 : DEG;
     uint32_t synd = 0;
-    final_edges_s<C, I>(synd, th, std::make_integer_sequence<int, NCORE>{});
+    if constexpr (CORE) final_edges_s<C, I>(synd, th, std::make_integer_sequence<int, NCORE>{});
     if constexpr (I >= 4) {
         float2 m;
         m.x = *reinterpret_cast<const float *>(th.smem + C::mags_base(I) + th.r4);
@@ -543,21 +557,78 @@ __device__ __forceinline__ void final_row_s(const Th<C> &th, int *flag)
         const uint32_t bits = load_bits<C, I>(th.smem + C::bits_base(I) + th.r4);
         const bool isidx = ((bits ^ ((uint32_t)(DEG - 1) << C::idx_shift(I))) & C::idx_mask(I)) == 0;
         const float lr = record_lr(m, isidx, bits << 31);
-        const float x = __fadd_rn(__fadd_rn(__ldg(th.llr + (C::kb + I - 2) * C::ZC), 0.0f), lr);
+        const float x = __fadd_rn(llr_e, lr);
         const bool hb1 = x <= 0.f;
         const uint32_t hb = __ballot_sync(0xffffffffu, hb1);
         if ((th.r & 31) == 0) reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + th.tile] = hb;
         synd ^= hb1 ? 1u : 0u;
     }
-    if (synd) flag[0] = 1;
+    if (CORE && synd) flag[0] = 1;
+    asm volatile("" ::: "memory");  // rows stay in program order (register pressure)
 }
-template <class C, int SUB, int O = 0>
-__device__ __forceinline__ void final_pass_s(const Th<C> &th, int *flag)
+// The channel LLRs of all extension variables of the group are requested up front: one exposed L2 latency
+// per final pass instead of one per row.
+template <class C, int SUB, bool CORE, int... O>
+__device__ __forceinline__ void final_pass_s(const Th<C> &th, int *flag, std::integer_sequence<int, O...>)
 {
-    if constexpr (O < kRows<C>.n[SUB]) {
-        final_row_s<C, kRows<C>.item[SUB][O]>(th, flag);
-        asm volatile("" ::: "memory");
-        final_pass_s<C, SUB, O + 1>(th, flag);
+    const float llr_e[] = {load_ext_llr<C, kRows<C>.item[SUB][O], true>(th)...};  // -0.0 -> +0.0
+    (final_row_s<C, kRows<C>.item[SUB][O], CORE>(th, flag, llr_e[O]), ...);
+}
+
+// ---- Final syndrome on bit-packed hard decisions (:134-143), for Zc a multiple of 32.
+// The hard decisions LQ <= 0 of the core column-blocks are ballot-packed into tiles words per column-block
+// (stored twice in a row, so that word index w + q needs no modulo); the syndrome word w of row-block i is then
+// the XOR over its core edges of bits [32 w + P, 32 w + P + 32) of the column's Zc-bit vector, i.e. a funnel shift
+// of two neighbouring words, XOR the packed hard bits of its extension column: Zc/32 lanes per row-block
+// instead of Zc threads, 2 shared-memory words per edge and syndrome word instead of 32.
+template <class C> struct FinalTab {
+    uint16_t start[C::nrows + 1];
+    uint16_t e[C::nnz];  // core edges only: col | (P / 32) << 5 | (P % 32) << 9
+};
+template <class C> constexpr FinalTab<C> make_final_tab()
+{
+    FinalTab<C> t{};
+    int n = 0;
+    for (int i = 0; i < C::nrows; ++i) {
+        t.start[i] = (uint16_t)n;
+        const int ncore = (i >= 4) ? C::deg(i) - 1 : C::deg(i);
+        for (int k = 0; k < ncore; ++k) {
+            const int e = C::G::rowptr(i) + k;
+            t.e[n++] = (uint16_t)(C::G::col(e) | ((C::P(e) / 32) << 5) | ((C::P(e) % 32) << 9));
+        }
+    }
+    t.start[C::nrows] = (uint16_t)n;
+    return t;
+}
+template <class C> __constant__ FinalTab<C> kFinalTab = make_final_tab<C>();
+
+template <class C> constexpr bool kFinalPacked = NRLDPC_FINAL_PACKED && C::ZC % 32 == 0 && 2 * C::tiles * C::ncore * 4 <= 4 * C::LQS * 4;
+
+// step 1 (all warps, after the last variable pass): pack the hard decisions of this warp group's columns
+template <class C> __device__ __forceinline__ void final_pack(int sub, const Th<C> &th, uint32_t *hbw)
+{
+    const int lane = th.r & 31;
+    for (int j = sub; j < C::ncore; j += C::S) {
+        const float x = *reinterpret_cast<const float *>(th.smem + C::lq_base(j) + th.r4);
+        const uint32_t word = __ballot_sync(0xffffffffu, x <= 0.f);
+        if (lane == 0) hbw[j * 2 * C::tiles + th.tile] = hbw[j * 2 * C::tiles + C::tiles + th.tile] = word;
+    }
+}
+// step 2 (after a barrier): warp `warp` checks row-blocks warp, warp + nwarps, ...; lane w < tiles owns syndrome word w
+template <class C> __device__ __forceinline__ void final_syndrome(int warp, int lane, const uint32_t *hbw, const uint32_t *ext, int *flag)
+{
+    for (int i = warp; i < C::nrows; i += C::nwarps) {
+        const int e0 = kFinalTab<C>.start[i], e1 = kFinalTab<C>.start[i + 1];
+        if (lane < C::tiles) {
+            uint32_t acc = (i >= 4) ? ext[(i - 4) * C::tiles + lane] : 0u;
+#pragma unroll 4
+            for (int e = e0; e < e1; ++e) {
+                const uint32_t t = kFinalTab<C>.e[e];
+                const uint32_t *v = hbw + (t & 31u) * (2 * C::tiles) + ((t >> 5) & 15u) + lane;
+                acc ^= __funnelshift_r(v[0], v[1], t >> 9);
+            }
+            if (acc) flag[0] = 1;
+        }
     }
 }
 
@@ -566,7 +637,8 @@ template <class C, bool ET, bool B0, bool FIRST, int SUB = 0>
 __device__ __forceinline__ void run_cn(int sub, const DecArgs &a, const Th<C> &th, int *flag)
 {
     if constexpr (SUB < C::S) {
-        if (sub == SUB) cn_pass_s<C, ET, B0, FIRST, SUB>(a, th, flag, load_row<C, kRows<C>.item[SUB][0], FIRST>(th), load_ext_llr<C, kRows<C>.item[SUB][0], ET>(th));
+        if (sub == SUB) cn_pass_s<C, ET, B0, FIRST, SUB>(a, th, flag, load_row<C, kRows<C>.item[SUB][0], FIRST>(th), load_ext_llr<C, kRows<C>.item[SUB][0], ET>(th),
+                                                        load_ext_llr<C, kRows<C>.item[SUB][kRows<C>.n[SUB] > 1 ? 1 : 0], ET>(th));
         else run_cn<C, ET, B0, FIRST, SUB + 1>(sub, a, th, flag);
     }
 }
@@ -578,12 +650,12 @@ __device__ __forceinline__ void run_vn(int sub, const Th<C> &th)
         else run_vn<C, SUB + 1>(sub, th);
     }
 }
-template <class C, int SUB = 0>
+template <class C, bool CORE = true, int SUB = 0>
 __device__ __forceinline__ void run_final(int sub, const Th<C> &th, int *flag)
 {
     if constexpr (SUB < C::S) {
-        if (sub == SUB) final_pass_s<C, SUB>(th, flag);
-        else run_final<C, SUB + 1>(sub, th, flag);
+        if (sub == SUB) final_pass_s<C, SUB, CORE>(th, flag, std::make_integer_sequence<int, kRows<C>.n[SUB]>{});
+        else run_final<C, CORE, SUB + 1>(sub, th, flag);
     }
 }
 
@@ -649,7 +721,10 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     if (pf) prefetch_l2(a.llr + (size_t)blockIdx.x * C::N, C::N * 4);
     for (int cb = blockIdx.x; cb < a.B; cb += gridDim.x) {
         th.llr = a.llr + (size_t)cb * C::N + th.r;
+#ifndef NRLDPC_EXP_NO_PF
         if (pf && cb + (int)gridDim.x < a.B) prefetch_l2(a.llr + (size_t)(cb + gridDim.x) * C::N, C::N * 4);
+
+#endif
 
         // ---- init: records = 0 (Lr = 0, :101), LQ = LLRin (:94) with the punctured columns at 0 (:43)
         {
@@ -661,7 +736,11 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
             for (int t = tid; t < 2 * C::LQS; t += NT) reinterpret_cast<float *>(smem + C::lq_base(0))[t] = 0.f;
             if (tid < 2) s_flag[tid] = 0;
             for (int j = 2 + sub; j < C::ncore; j += C::S) {
+#ifdef NRLDPC_EXP_NO_INIT_LLR
+                const float v = 1.0f;
+#else
                 const float v = __fadd_rn(__ldg(th.llr + (j - 2) * ZC), 0.0f);  // -0.0 -> +0.0
+#endif
                 float *dst = reinterpret_cast<float *>(smem + C::lq_base(j) + th.r4);
                 *dst = v;
                 if (th.tile == 0) dst[ZC] = v;
@@ -692,12 +771,23 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
             __syncthreads();
         }
         bool ok = et_done;
+#ifndef NRLDPC_EXP_NO_FINAL
         if (!et_done) {
             int *flag = &s_flag[it & 1];
-            run_final<C>(sub, th, flag);
+            if constexpr (kFinalPacked<C>) {
+                // the records of the core row-blocks 0-3 are dead after the last variable pass: their mag1 rows hold the packed words
+                uint32_t *hbw = reinterpret_cast<uint32_t *>(smem + C::mags_base(0));
+                final_pack<C>(sub, th, hbw);
+                run_final<C, false>(sub, th, flag);  // hard bits of the extension columns
+                __syncthreads();
+                final_syndrome<C>(warp, lane, hbw, reinterpret_cast<const uint32_t *>(smem + C::off_ext), flag);
+            } else {
+                run_final<C>(sub, th, flag);
+            }
             __syncthreads();
             ok = (*flag == 0);
         }
+#endif
 
         // ---- outputs
         if (tid == 0) {
@@ -716,7 +806,13 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
                 out[C::ncore * ZC + n] = (int8_t)((ext[i4 * C::tiles + (r >> 5)] >> (r & 31)) & 1u);
             }
         }
-        if (a.info) {
+#ifndef NRLDPC_EXP_NO_OUT
+        if (kFinalPacked<C> && a.info && !et_done) {
+            // the packed hard decisions of the final syndrome are the info words (K = kb Zc, Zc a multiple of 32)
+            constexpr int nwords = C::kb * C::tiles;
+            const uint32_t *hbw = reinterpret_cast<const uint32_t *>(smem + C::mags_base(0));
+            for (int n = tid; n < nwords; n += NT) a.info[(size_t)cb * nwords + n] = hbw[(n / C::tiles) * 2 * C::tiles + n % C::tiles];
+        } else if (a.info) {
             constexpr int nwords = (C::K + 31) / 32;
             for (int w = (tid >> 5); w < nwords; w += C::nwarps) {
                 const int n = min(32 * w + lane, C::K - 1), j = n / ZC, c = n - j * ZC;
@@ -726,6 +822,7 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
                 if (lane == 0) a.info[(size_t)cb * nwords + w] = word;
             }
         }
+#endif
         __syncthreads();  // the state is re-initialised for the next codeblock
     }
 }
