@@ -285,8 +285,8 @@ def run_ours(args):
         out["roofline_onchip"] = {"bound": "issue_slots", "achieved": per_gpu_cbs * WARP_INSTR_PER_CB / 1e9,
                                   "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": per_gpu_cbs * WARP_INSTR_PER_CB / issue_peak,
                                   "warp_instr_per_codeblock": WARP_INSTR_PER_CB,
-                                  "source": "smsp__inst_executed.sum of profiles/prof_r1h.ncu-rep / 592 codeblocks; ALU pipe 74 %, "
-                                            "issue 81 %, smem wavefronts 63 % busy in that capture"}
+                                  "source": "smsp__inst_executed.sum of profiles/prof_r1i.ncu-rep / 592 codeblocks; ALU pipe 68 %, "
+                                            "issue 78 %, smem wavefronts 62 % busy in that capture"}
         if not args.no_cpu and world == 1:   # reported at N=1 only (rank 0); ~10 s of CPU work on all host cores
             ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             gbps, threads, n, sps = cpu_reference_run(1, 0, sample_cbs=max(400 * ncores, 256))
@@ -306,7 +306,7 @@ def ctypes_int():
 # From the committed `ncu --set full` capture (profiles/r1_decode_spec_ncu_summary.md, 592 codeblocks):
 # dram__bytes_read.sum + dram__bytes_write.sum = 60.151 MB + 0.292 MB; smsp__inst_executed.sum = 495.07 M
 TRAFFIC_BYTES_PER_CB = (60151296 + 291840) / 592
-WARP_INSTR_PER_CB = 495071248 / 592
+WARP_INSTR_PER_CB = 466162704 / 592
 
 
 def main():
