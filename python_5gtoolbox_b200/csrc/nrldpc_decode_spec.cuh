@@ -74,6 +74,9 @@ constexpr int kMaxS = 16;  // warp groups per r-tile
 #ifndef NRLDPC_PF_LLR2
 #define NRLDPC_PF_LLR2 1  // channel LLR of a check row's extension variable fetched two rows ahead (L2 latency) instead of one
 #endif
+#ifndef NRLDPC_PF_VLLR
+#define NRLDPC_PF_VLLR 2  // channel LLR of a core column fetched this many columns ahead in the variable pass (1 or 2)
+#endif
 #ifndef NRLDPC_FINAL_PACKED
 #define NRLDPC_FINAL_PACKED 1  // final syndrome on bit-packed hard decisions (lifting sizes that are a multiple of 32)
 #endif
@@ -521,17 +524,23 @@ template <class C, int J> __device__ __forceinline__ float load_col_llr(const Th
 // The columns of warp group SUB.  A column's posterior is stored after the NEXT column's records have
 // been read (same aliasing argument as in cn_pass_s), its channel LLR is fetched one column ahead.
 template <class C, int SUB, int O = 0>
-__device__ __forceinline__ void vn_pass_s(const Th<C> &th, const float lv_cur, const float lq_prev)
+__device__ __forceinline__ void vn_pass_s(const Th<C> &th, const float lv_cur, const float lq_prev, const float lv_nxt_in = 0.f)
 {
     if constexpr (O < kCols<C>.n[SUB]) {
 #if NRLDPC_GROUP_SYNC_VN > 0
         if constexpr (O > 0 && O % NRLDPC_GROUP_SYNC_VN == 0) group_sync<C, SUB>();
 #endif
-        float lv_nxt = 0.f;
+#if NRLDPC_PF_VLLR == 2
+        const float lv_nxt = lv_nxt_in;
+        float lv_nn = 0.f;
+        if constexpr (O + 2 < kCols<C>.n[SUB]) lv_nn = load_col_llr<C, kCols<C>.item[SUB][O + 2]>(th);
+#else
+        float lv_nxt = 0.f, lv_nn = 0.f;
         if constexpr (O + 1 < kCols<C>.n[SUB]) lv_nxt = load_col_llr<C, kCols<C>.item[SUB][O + 1]>(th);
+#endif
         const float lq = vn_col_s<C, kCols<C>.item[SUB][O]>(th, lv_cur);
         if constexpr (O > 0) vn_store_s<C, kCols<C>.item[SUB][O - 1]>(th, lq_prev);
-        vn_pass_s<C, SUB, O + 1>(th, lv_nxt, lq);
+        vn_pass_s<C, SUB, O + 1>(th, lv_nxt, lq, lv_nn);
     } else if constexpr (O > 0) {
         vn_store_s<C, kCols<C>.item[SUB][O - 1]>(th, lq_prev);
     }
@@ -646,7 +655,8 @@ template <class C, int SUB = 0>
 __device__ __forceinline__ void run_vn(int sub, const Th<C> &th)
 {
     if constexpr (SUB < C::S) {
-        if (sub == SUB) vn_pass_s<C, SUB>(th, load_col_llr<C, kCols<C>.item[SUB][0]>(th), 0.f);
+        if (sub == SUB) vn_pass_s<C, SUB>(th, load_col_llr<C, kCols<C>.item[SUB][0]>(th), 0.f,
+                                          load_col_llr<C, kCols<C>.item[SUB][kCols<C>.n[SUB] > 1 ? 1 : 0]>(th));
         else run_vn<C, SUB + 1>(sub, th);
     }
 }
