@@ -25,6 +25,7 @@
 // Compile-time switches (NRLDPC_*) keep the measured alternatives buildable: tools/build_variant.sh.
 #pragma once
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <utility>
 
@@ -71,6 +72,9 @@ constexpr int kMaxS = 16;  // warp groups per r-tile
 #ifndef NRLDPC_GROUP_SYNC_VN
 #define NRLDPC_GROUP_SYNC_VN 0  // same, every this many columns of the variable pass
 #endif
+#ifndef NRLDPC_TWO_CTAS
+#define NRLDPC_TWO_CTAS 0  // two persistent CTAs per SM where two codeblock states fit in its shared memory (small Zc): the
+#endif                     // check pass of one could overlap the variable pass of the other -- measured: +1 % (BG1 Zc=176), -11 % (BG2 Zc=208)
 #ifndef NRLDPC_PF_LLR2
 #define NRLDPC_PF_LLR2 1  // channel LLR of a check row's extension variable fetched two rows ahead (L2 latency) instead of one
 #endif
@@ -115,7 +119,7 @@ template <int BGN, int ZC_> struct Code {
     static_assert(iLS >= 0 && ZC_ >= 64, "specialised kernels need a lifting size >= 64");
     static constexpr int nrows = G::rows, kb = G::kb, ncore = G::kb + 4, nnz = G::nnz;
     static constexpr int K = kb * ZC, N = (G::cols - 2) * ZC, Nfull = G::cols * ZC;
-    static constexpr int tiles = (ZC + 31) / 32, S = (32 / tiles) < kMaxS ? (32 / tiles) : kMaxS, nwarps = tiles * S;
+    static constexpr int tiles = (ZC + 31) / 32;
     static constexpr int LQS = ZC + 32;  // elements per rotated array: Zc + the 32 mirrored ones
     static constexpr int deg(int i) { return G::rowptr(i + 1) - G::rowptr(i); }
     static constexpr int P(int e) { return G::shift(iLS, e) % ZC; }
@@ -148,6 +152,11 @@ template <int BGN, int ZC_> struct Code {
     static constexpr int off_b8 = off_b16 + ((count(1) + 1) / 2) * LQS * 4;   // uint8 quads of rows interleaved
     static constexpr int off_ext = off_b8 + ((count(0) + 3) / 4) * LQS * 4;   // packed hard bits of the extension columns
     static constexpr int smem_bytes = (off_ext + (nrows - 4) * tiles * 4 + 15) & ~15;
+    // CTAs per SM: two when two codeblock states (+ 1 KB of system shared memory each) fit in the SM's 228 KB; each then
+    // runs 16 / tiles warp groups (at most 512 threads, so that two CTAs keep >= 64 registers per thread)
+    static constexpr int ctas = (NRLDPC_TWO_CTAS && 2 * (smem_bytes + 1024) <= 228 * 1024 && 16 / tiles >= 1) ? 2 : 1;
+    static constexpr int Smax = (ctas == 2 ? 16 : 32) / tiles;
+    static constexpr int S = Smax < kMaxS ? Smax : kMaxS, nwarps = tiles * S;
     static constexpr int lq_base(int j) { return off_lq + j * LQS * 4; }
     static constexpr int mags_base(int i) { return off_mags + i * LQS * 4; }  // mag1 of check 0; mag2 sits mag2_dist further
     static constexpr int bits_base(int i)  // the word of check r sits at bits_base(i) + 4 r
@@ -686,7 +695,7 @@ int num_sms()
 }
 
 template <class C, bool ET, bool B0>
-__global__ void __launch_bounds__(C::nwarps * 32, 1)
+__global__ void __launch_bounds__(C::nwarps * 32, C::ctas)
 decode_spec_kernel(const __grid_constant__ DecArgs a)
 {
     extern __shared__ __align__(16) char smem[];
@@ -843,7 +852,14 @@ int launch_spec(const DecArgs &a, int early_term, cudaStream_t s)
     static_assert(C::smem_bytes <= 227 * 1024 - 64, "codeblock state does not fit in shared memory");
     auto launch = [&](auto kern) -> int {
         NRLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
-        kern<<<std::min(a.B, num_sms()), C::nwarps * 32, C::smem_bytes, s>>>(a);
+        NRLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (getenv("NRLDPC_DEBUG")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::nwarps * 32, C::smem_bytes);
+            fprintf(stderr, "nrldpc: decode_spec<%d,%d> threads=%d smem=%d ctas/SM wanted=%d resident=%d\n", C::bgn, C::ZC,
+                    C::nwarps * 32, C::smem_bytes, C::ctas, nb);
+        }
+        kern<<<std::min(a.B, C::ctas * num_sms()), C::nwarps * 32, C::smem_bytes, s>>>(a);
         NRLDPC_CUDA(cudaGetLastError());
         return NRLDPC_OK;
     };

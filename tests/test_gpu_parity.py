@@ -211,6 +211,34 @@ def test_decode_headline_spec_kernel_vs_oracle(eng, oracle, bgn, Zc):
     assert np.array_equal(r["ck"][:8].cpu().numpy(), c) and np.array_equal(r["iters"][:8].cpu().numpy(), i)
 
 
+@pytest.mark.parametrize("bgn,Zc", [(1, 384), (2, 384), (1, 320), (2, 288), (1, 208), (2, 176)])
+def test_final_syndrome_single_flips(eng, oracle, bgn, Zc):
+    """The final syndrome of the specialised kernels (bit-packed for Zc % 32 == 0, per lifted row otherwise) and
+    its status bit: with L = 0 the decision is taken on the channel LLRs alone (LQ = LLR, punctured bits decide 1,
+    py5gphy/ldpc/nr_ldpc_decode.py:134-143), so a codeword whose 2 Zc punctured bits are ones passes and ONE
+    flipped LLR anywhere -- every core column-block, every extension column-block, first / last lifted index --
+    must fail; after L = 1, 2 iterations without early termination the same inputs follow the oracle bit for bit
+    (the packed decisions are also what is written as info bits)."""
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    rng = np.random.default_rng(7 * Zc + bgn)
+    ck = _rand_ck(rng, bgn, Zc, 1, fillers=False)
+    ck[0, :2 * Zc] = 1
+    dn = oracle.encode_batch(ck.copy(), bgn, Zc)[0]
+    ncol = N // Zc
+    pos = sorted({j * Zc + o for j in range(ncol) for o in (0, Zc - 1, int(rng.integers(0, Zc)))})
+    llr = np.tile(np.where(dn == 1, -4.0, 4.0).astype(np.float32), (len(pos) + 1, 1))
+    for b, n in enumerate(pos):
+        llr[b + 1, n] = -llr[b + 1, n]
+    for L in (0, 1, 2):
+        r = eng.decode_batch(llr, Zc, bgn, L, 0.75, 0.0, False, want_info=True)
+        c, s, i = oracle.decode_batch(llr, Zc, bgn, L, "min-sum", 0.75, 0.0, 0, np.float32)
+        assert np.array_equal(r["status"], s) and np.array_equal(r["ck"], c) and np.array_equal(r["iters"], i), L
+        info = np.unpackbits(r["info"].view(np.uint8), axis=1, bitorder="little")[:, :K]
+        assert np.array_equal(info, c[:, :K]), L
+        if L == 0:
+            assert bool(r["status"][0]) and not r["status"][1:].any()
+
+
 def test_decode_spec_and_table_kernels_agree(eng):
     """The table-driven kernel (NRLDPC_NO_SPEC=1, read once per process -> subprocess) and the
     specialised kernel give identical outputs on the same BG1 Zc=384 batch."""
