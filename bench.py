@@ -228,6 +228,9 @@ def run_ours(args):
 
     # ---- e2e through the host-buffer C-ABI entry point, pinned host memory
     Be = min(args.e2e_batch, B)
+    # pinned buffers are placed on the NUMA node next to this rank's GPU (process affinity while they are allocated)
+    cores_before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    bound = engine.bind_host_to_device(local)
     h_llr = torch.empty((Be, N_CODED), dtype=torch.float32).pin_memory()
     h_llr.copy_(llr[:Be])
     h_info = torch.empty((Be, (K_INFO + 31) // 32), dtype=torch.int32).pin_memory()
@@ -250,6 +253,8 @@ def run_ours(args):
         dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
     e2e_val = world * Be * e_steps * K_INFO / float(e_dt.item()) / 1e9
     assert torch.equal(h_info.to(dev), info[:Be]), "host path and device path disagree"
+    if bound is not None:
+        os.sched_setaffinity(0, cores_before)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -267,7 +272,8 @@ def run_ours(args):
                        "block_error_rate": cnt[1] / cnt[0], "mean_iters": cnt[3] / cnt[0], "parity_ok_frac": cnt[4] / cnt[0],
                        "other_runs_1gpu_untimed_region": extra},
             "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": Be * N_CODED * 4,
-                    "d2h_bytes_per_step": Be * ((K_INFO + 31) // 32 * 4 + 1 + 4), "codeblocks_per_step": Be},
+                    "d2h_bytes_per_step": Be * ((K_INFO + 31) // 32 * 4 + 1 + 4), "codeblocks_per_step": Be,
+                    "host_cores_bound_to_gpu_numa_node": len(bound) if bound is not None else None},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": TRAFFIC_BYTES_PER_CB * B, "peak_source": peak_src,

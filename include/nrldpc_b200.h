@@ -109,7 +109,14 @@ int nrldpc_decode_soft_ref_host(const void *llr, int is_f64, int B, int bgn, int
  */
 int nrldpc_decode_bf_csr_host(const double *llr, int B, int M, int Nv, const int32_t *rowptr,
                               const int32_t *colidx, int max_iter, int8_t *ck, uint8_t *status, int32_t *iters);
-/* nr_decode_ldpc(..., algo='BF') (py5gphy/ldpc/nr_ldpc_decode.py:43,65-67): llr [B,N], ck [B,N']. */
+/*
+ * nr_decode_ldpc(..., algo='BF') (py5gphy/ldpc/nr_ldpc_decode.py:43,65-67) on the quasi-cyclic bit-flipping kernel
+ * (state of a codeblock resident in shared memory): llr [B,N] (float32, or float64 when is_f64), ck [B,N'] int8,
+ * status[b] = 1 when a zero syndrome was reached, iters[b] = the iteration index at which it was (else max_iter).
+ * nrldpc_decode_bf takes device pointers and a stream; nrldpc_decode_bf_host host buffers (synchronous).
+ */
+int nrldpc_decode_bf(const void *d_llr, int is_f64, int B, int bgn, int Zc, int max_iter, int8_t *d_ck,
+                     uint8_t *d_status, int32_t *d_iters, void *stream);
 int nrldpc_decode_bf_host(const double *llr, int B, int bgn, int Zc, int max_iter, int8_t *ck, uint8_t *status,
                           int32_t *iters);
 

@@ -48,6 +48,7 @@ def _declare(L):
         "nrldpc_decode_soft_ref_host": (i, [p, i, i, i, i, i, i, d, d, i, p, p, p]),
         "nrldpc_decode_bf_csr_host": (i, [p, i, i, i, p, p, i, p, p, p]),
         "nrldpc_decode_bf_host": (i, [p, i, i, i, i, p, p, p]),
+        "nrldpc_decode_bf": (i, [p, i, i, i, i, i, p, p, p, p]),
         "nrldpc_awgn_llr": (i, [p, ll, f, ull, ull, p, p]),
         "nrldpc_random_bits": (i, [p, ll, ull, ull, p]),
         "nrldpc_awgn_llr_rows": (i, [p, ll, ll, f, ull, ll, ll, p, p]),

@@ -341,15 +341,41 @@ int nrldpc_decode_bf_csr_host(const double *llr, int B, int M, int Nv, const int
     return bf_csr_host(llr, B, M, Nv, rowptr, colidx, 0, max_iter, ck, status, iters);
 }
 
+int nrldpc_decode_bf(const void *d_llr, int is_f64, int B, int bgn, int Zc, int max_iter, int8_t *d_ck,
+                     uint8_t *d_status, int32_t *d_iters, void *stream)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    if (B < 0 || max_iter < 0 || !d_llr || !d_ck) { set_error("decode_bf: bad argument"); return NRLDPC_EINVAL; }
+    return launch_bf_qc(*c, d_llr, is_f64, B, max_iter, d_ck, d_status, d_iters, (cudaStream_t)stream);
+}
+
 int nrldpc_decode_bf_host(const double *llr, int B, int bgn, int Zc, int max_iter, int8_t *ck, uint8_t *status,
                           int32_t *iters)
 {
     const QcCfg *c = get_cfg(bgn, Zc);
     if (!c) return NRLDPC_EINVAL;
-    const int nnz = (bgn == 1 ? 316 : 197) * Zc;
-    std::vector<int32_t> rowptr(c->M + 1), colidx(nnz);
-    build_csr(bgn, Zc, rowptr.data(), colidx.data());
-    return bf_csr_host(llr, B, c->M, c->Nfull, rowptr.data(), colidx.data(), 2 * Zc, max_iter, ck, status, iters);
+    if (B < 0 || max_iter < 0 || !llr || !ck) { set_error("decode_bf: bad argument"); return NRLDPC_EINVAL; }
+    if (B == 0) return NRLDPC_OK;
+    // chunks of <= 256 MB of LLRs through scratch buffers on the default stream
+    const size_t per_cb = (size_t)c->N * 8;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)256 << 20) / per_cb));
+    DevBuf d_llr, d_ck, d_st, d_it;
+    NRLDPC_CUDA(d_llr.alloc((size_t)chunk * per_cb));
+    NRLDPC_CUDA(d_ck.alloc((size_t)chunk * c->Nfull));
+    NRLDPC_CUDA(d_st.alloc((size_t)chunk));
+    NRLDPC_CUDA(d_it.alloc((size_t)chunk * 4));
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        NRLDPC_CUDA(cudaMemcpy(d_llr.p, llr + (size_t)b0 * c->N, (size_t)nb * per_cb, cudaMemcpyHostToDevice));
+        if (int rc = launch_bf_qc(*c, d_llr.p, 1, nb, max_iter, d_ck.as<int8_t>(), d_st.as<uint8_t>(),
+                                  d_it.as<int32_t>(), 0))
+            return rc;
+        NRLDPC_CUDA(cudaMemcpy(ck + (size_t)b0 * c->Nfull, d_ck.p, (size_t)nb * c->Nfull, cudaMemcpyDeviceToHost));
+        if (status) NRLDPC_CUDA(cudaMemcpy(status + b0, d_st.p, (size_t)nb, cudaMemcpyDeviceToHost));
+        if (iters) NRLDPC_CUDA(cudaMemcpy(iters + b0, d_it.p, (size_t)nb * 4, cudaMemcpyDeviceToHost));
+    }
+    return NRLDPC_OK;
 }
 
 }  // extern "C"

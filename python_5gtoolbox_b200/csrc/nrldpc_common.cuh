@@ -99,4 +99,7 @@ int launch_bf_csr(const double *d_llr, int B, int M, int Nv, int E, const int32_
                   const int32_t *d_cptr, const int32_t *d_cedge, int prepend, int max_iter, int32_t *d_work,
                   int8_t *d_ck, uint8_t *d_status, int32_t *d_iters, cudaStream_t s);
 
+int launch_bf_qc(const QcCfg &cfg, const void *d_llr, int is_f64, int B, int max_iter, int8_t *d_ck,
+                 uint8_t *d_status, int32_t *d_iters, cudaStream_t s);
+
 }  // namespace nrldpc

@@ -162,6 +162,20 @@ def decode_csr_batch(llr, rowptr, colidx, Nv, L, algo="min-sum", alpha=1.0, beta
 def decode_bf_batch(llr, Zc, bgn, L):
     """nr_decode_ldpc(..., algo='BF') for B codeblocks (py5gphy/ldpc/ldpc_decoder_bit_flipping.py:5-73)."""
     K, N, Nf, M = dims(bgn, Zc)
+    if _is_torch(llr):
+        # device path: float32 / float64 CUDA tensor in, CUDA tensors out, async on the current stream
+        import torch
+        assert llr.is_cuda and llr.dtype in (torch.float32, torch.float64) and llr.is_contiguous()
+        assert llr.ndim == 2 and llr.shape[1] == N
+        B, dev = llr.shape[0], llr.device
+        ck = torch.empty((B, Nf), dtype=torch.int8, device=dev)
+        status = torch.empty((B,), dtype=torch.uint8, device=dev)
+        iters = torch.empty((B,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nrldpc_decode_bf(llr.data_ptr(), int(llr.dtype == torch.float64), B, bgn, int(Zc),
+                                                   int(L), ck.data_ptr(), status.data_ptr(), iters.data_ptr(),
+                                                   _stream_ptr()), "decode_bf")
+        return ck, status, iters
     llr = np.ascontiguousarray(np.atleast_2d(llr), np.float64)
     assert llr.shape[1] == N
     B = llr.shape[0]
@@ -186,6 +200,36 @@ def decode_bf_csr_batch(llr, rowptr, colidx, Nv, L):
                                                     colidx.ctypes.data, int(L), ck.ctypes.data, status.ctypes.data,
                                                     iters.ctypes.data), "decode_bf_csr")
     return ck, status.astype(bool), iters
+
+
+# ------------------------------------------------------------------ host placement for the host-buffer entry points
+
+def bind_host_to_device(device_index=0):
+    """Pin this process to the CPU cores next to CUDA device `device_index` (NVML's ideal affinity, intersected with
+    the cores the container allows), so that pinned host buffers allocated afterwards land on the GPU's NUMA node
+    and the host-buffer entry points do not pull LLRs across the socket interconnect.  One process per GPU, called
+    before any pinned allocation.  Returns the core list now in force, or None when nothing was changed (no NVML,
+    no sched_setaffinity, or the ideal cores are outside the allowed set)."""
+    import os
+    if not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+        ncpu = max(os.cpu_count() or 1, max(os.sched_getaffinity(0)) + 1)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1}
+        want = sorted(ideal & set(os.sched_getaffinity(0)))
+        if not want:
+            return None
+        os.sched_setaffinity(0, want)
+        return want
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------ device-side Monte-Carlo helpers (torch tensors)

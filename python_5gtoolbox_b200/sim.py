@@ -150,12 +150,12 @@ class CudaBackend:
                 llr = torch.empty(dn.shape, dtype=torch.float32, device=self.device)
                 _lib.check(L_.nrldpc_awgn_llr_rows(dn.data_ptr(), mm, dn.shape[1], float(snr_db), seed, first + i0 * stride,
                                                    stride, llr.data_ptr(), s), "awgn")
-                if algo in ('BF', 'BP'):
+                if algo == 'BF':   # quasi-cyclic bit-flipping kernel, device-resident like the min-sum chain
+                    ck, _, it = engine.decode_bf_batch(llr, Zc, bgn, L)
+                    fails += int(engine.count_errors(blk, ck, K, it)[1].item())
+                elif algo == 'BP':
                     h = llr.cpu().numpy().astype(np.float64)
-                    if algo == 'BF':
-                        ck, _, _ = engine.decode_bf_batch(h, Zc, bgn, L)
-                    else:
-                        ck, _, _ = engine.decode_ref_batch(h, Zc, bgn, L, 'BP', 1, 0, True, f64=True)
+                    ck, _, _ = engine.decode_ref_batch(h, Zc, bgn, L, 'BP', 1, 0, True, f64=True)
                     fails += int((ck[:, :K] != blk.cpu().numpy()).any(axis=1).sum())
                 else:
                     r = engine.decode_batch(llr, Zc, bgn, L, alpha, beta, True)

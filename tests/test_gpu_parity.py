@@ -378,6 +378,43 @@ def test_bf_kat(eng, oracle, case):
     assert np.array_equal(ck[0], hex_to_bits(hck, Nf)) and bool(st[0]) == status
 
 
+def test_bf_qc_kernel_all_lifting_sizes(eng, oracle):
+    """The quasi-cyclic bit-flipping kernel (shared-memory state) against the oracle's ldpc_decoder_BF and against
+    the generic CSR kernel on getH's matrix, every lifting size x both base graphs; device float32 path too."""
+    import torch
+    rng = np.random.default_rng(11)
+    for bgn in (1, 2):
+        for Zc in ZLIST:
+            B = 3 if Zc > 64 else 6
+            dn = oracle.encode_batch(_rand_ck(rng, bgn, Zc, B, fillers=False), bgn, Zc)
+            llr = _awgn(rng, dn, 5.5 if bgn == 1 else 3.5).astype(np.float64)
+            llr[0, :: 7] = 0.0   # LLR == 0 decides bit 0 (:41-43)
+            L = 9
+            ck, st, it = eng.decode_bf_batch(llr, Zc, bgn, L)
+            rp, ci = eng.csr(Zc, bgn)
+            K, N, Nf, M = eng.dims(bgn, Zc)
+            full = np.concatenate([np.zeros((B, 2 * Zc)), llr], axis=1)
+            ck2, st2, it2 = eng.decode_bf_csr_batch(full, rp, ci, Nf, L)
+            assert np.array_equal(ck, ck2) and np.array_equal(st, st2) and np.array_equal(it, it2), (bgn, Zc)
+            if Zc <= 64 or Zc in (208, 384):
+                for b in range(B):
+                    _, c, s, i = oracle.nr_decode_ldpc(llr[b], Zc, bgn, L, "BF")
+                    assert np.array_equal(ck[b], c) and bool(st[b]) == s and int(it[b]) == i, (bgn, Zc, b)
+            d = eng.decode_bf_batch(torch.from_numpy(llr.astype(np.float32)).cuda(), Zc, bgn, L)
+            assert np.array_equal(d[0].cpu().numpy(), ck) and np.array_equal(d[1].cpu().numpy().astype(bool), st)
+            assert np.array_equal(d[2].cpu().numpy(), it)
+    # a converging and a non-converging batch at the headline size
+    dn = oracle.encode_batch(_rand_ck(rng, 1, 384, 64, fillers=False), 1, 384)
+    for snr in (7.5, 3.0):
+        llr = _awgn(rng, dn, snr).astype(np.float64)
+        ck, st, it = eng.decode_bf_batch(llr, 384, 1, 20)
+        for b in (0, 63):
+            _, c, s, i = oracle.nr_decode_ldpc(llr[b], 384, 1, 20, "BF")
+            assert np.array_equal(ck[b], c) and bool(st[b]) == s and int(it[b]) == i
+        if snr > 7:
+            assert st.all() and np.array_equal(ck[:, 2 * 384:], dn)
+
+
 def test_generic_h_toy_matrix(eng, oracle):
     """Arbitrary (non-QC) H: the toy 4x6 matrix style of ldpc_decoder_bit_flipping.py:115-131."""
     H = np.array([[1, 1, 0, 1, 0, 0], [0, 1, 1, 0, 1, 0], [1, 0, 0, 0, 1, 1], [0, 0, 1, 1, 0, 1]], "i1")
