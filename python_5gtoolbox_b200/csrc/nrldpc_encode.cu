@@ -8,41 +8,13 @@
 //   L1 = A ck (4 row-blocks), L2 = sum L1, pc1 = roll(L2, s), pc2/pc4 from pc1, pc3 from pc4 (BG1) or
 //   pc2 (BG2), extension parity pe = C [ck; pc].
 #include "nrldpc_common.cuh"
+#include "nrldpc_bits.cuh"
 
 namespace nrldpc {
 
 namespace {
 
 constexpr int kEncThreads = 256;
-
-// 32 bits of the Zc-bit circular vector v starting at bit position `pos` (0 <= pos < Zc), i.e.
-// result bit t = v[(pos + t) mod Zc].  v has W = ceil(Zc/32) words plus one zero pad word, and the
-// bits at positions >= Zc of the last word are zero.
-__device__ __forceinline__ uint32_t circ_window(const uint32_t *v, int pos, int Zc)
-{
-    if (Zc >= 32) {
-        const int q = pos >> 5, sh = pos & 31;
-        uint32_t out = __funnelshift_r(v[q], v[q + 1], sh);
-        const int n1 = Zc - pos;  // bits available before the wrap
-        if (n1 < 32) out = (out & ((1u << n1) - 1u)) | (v[0] << n1);
-        return out;
-    }
-    // Zc < 32: replicate the vector until it covers pos + 32 bits
-    unsigned long long rep = v[0];
-    for (int len = Zc; len < 64; len <<= 1) rep |= rep << len;
-    return (uint32_t)(rep >> pos);
-}
-
-// word w of (circulant block with shift P) @ v :  out[r] = v[(r + P) mod Zc], r = 32w .. 32w+31
-__device__ __forceinline__ uint32_t rot_word(const uint32_t *v, int P, int w, int Zc)
-{
-    int pos = 32 * w + P;
-    if (pos >= Zc) pos -= Zc;  // 32w < Zc and P < Zc
-    uint32_t out = circ_window(v, pos, Zc);
-    const int nv = Zc - 32 * w;  // valid bits of this word
-    if (nv < 32) out &= (1u << nv) - 1u;
-    return out;
-}
 
 __device__ __forceinline__ int find_edge(const QcCfg &c, int i, int j)
 {
@@ -53,7 +25,7 @@ __device__ __forceinline__ int find_edge(const QcCfg &c, int i, int j)
 
 __global__ void __launch_bounds__(kEncThreads)
 encode_kernel(const __grid_constant__ QcCfg c, int8_t *__restrict__ ck, int B, int G, int fix_fillers,
-              int8_t *__restrict__ dn)
+              int8_t *__restrict__ dn, int vec)
 {
     extern __shared__ uint32_t smem[];
     const int Zc = c.Zc, W = c.tiles, Wp = W + 1;
@@ -69,8 +41,36 @@ encode_kernel(const __grid_constant__ QcCfg c, int8_t *__restrict__ ck, int B, i
     for (int t = threadIdx.x; t < g_cnt * slot; t += kEncThreads) smem[t] = 0;
     __syncthreads();
 
-    // A. pack the K input bits: one warp per (codeblock, column-block, word)
-    for (int it = warp; it < g_cnt * c.kb * W; it += nwarps) {
+    // A. pack the K input bits.  Zc % 16 == 0 and 16-byte aligned rows (vec): one thread per 16 input bytes, one
+    // 128-bit load -> 16 codeword bits + 16 filler-mask bits written as a half word; otherwise one warp per
+    // (codeblock, column-block, word) with a ballot.
+    const int H = Zc >> 4;  // 16-bit chunks per column-block (vec)
+    // vec thread mapping: thread = (row tj, chunk h) of the [rows][H] array of 16-byte chunks, RYv rows per sweep;
+    // rows of consecutive codeblocks are contiguous in memory, so a sweep reads one contiguous range and the only
+    // divisions are by the compile-time kb / (ncols - 2) of the base graph
+    const int tj = vec ? (int)threadIdx.x / H : 0, h = (int)threadIdx.x - tj * H, RYv = vec ? kEncThreads / H : 1;
+    if (vec) {
+        for (int R = tj; R < g_cnt * c.kb && tj < RYv; R += RYv) {
+            const int g = c.bgn == 1 ? R / 22 : R / 10, j = R - g * c.kb;
+            uint4 *src = reinterpret_cast<uint4 *>(ck + (long long)(cb0 + g) * c.K + j * Zc + 16 * h);
+            uint4 x = *src;
+            uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+            uint32_t bits = 0, fmask = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                // bytes equal to 0xFF (-1): fillers when j >= 2 (nr_ldpc_encode.py:32-35)
+                uint32_t m = (j >= 2) ? (((xs[q] & 0x7f7f7f7fu) + 0x01010101u) & xs[q] & 0x80808080u) >> 7 : 0u;
+                const uint32_t b = xs[q] & 0x01010101u & ~m;
+                bits |= ((b * 0x01020408u) >> 24) << (4 * q);
+                fmask |= ((m * 0x01020408u) >> 24) << (4 * q);
+                xs[q] &= ~(m * 0xffu);
+            }
+            reinterpret_cast<uint16_t *>(V(g, j))[h] = (uint16_t)bits;
+            reinterpret_cast<uint16_t *>(FM(g, j))[h] = (uint16_t)fmask;
+            if (fmask && fix_fillers) *src = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+        }
+    }
+    for (int it = vec ? 0x7fffffff : warp; it < g_cnt * c.kb * W; it += nwarps) {
         const int g = it / (c.kb * W), rem = it % (c.kb * W), j = rem / W, w = rem % W;
         const int r = 32 * w + lane;
         int val = 0;
@@ -139,6 +139,22 @@ encode_kernel(const __grid_constant__ QcCfg c, int8_t *__restrict__ ck, int B, i
 
     // D. unpack dn = codeword without the first 2Zc bits; -1 at filler positions (:31-37,:47-48)
     const int nout = c.ncols - 2;
+    if (vec) {
+        for (int R = tj; R < g_cnt * nout && tj < RYv; R += RYv) {
+            const int g = c.bgn == 1 ? R / 66 : R / 50, jo = R - g * nout, j = jo + 2;
+            const uint32_t bits = reinterpret_cast<const uint16_t *>(V(g, j))[h];
+            const uint32_t fm = (j < kb) ? reinterpret_cast<const uint16_t *>(FM(g, j))[h] : 0u;
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t b = (((bits >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;
+                const uint32_t m = (((fm >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;
+                o[q] = b | (m * 0xffu);
+            }
+            *reinterpret_cast<uint4 *>(dn + (long long)(cb0 + g) * c.N + jo * Zc + 16 * h) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        return;
+    }
     for (int it = warp; it < g_cnt * nout * W; it += nwarps) {
         const int g = it / (nout * W), rem = it % (nout * W), j = 2 + rem / W, w = rem % W;
         const int r = 32 * w + lane;
@@ -161,7 +177,8 @@ int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t
     int G = 1;
     while (G < 16 && (G * 2) * slot_bytes <= 48 * 1024 && G * cfg.nrows * cfg.tiles < 2 * kEncThreads) G *= 2;
     const int grid = (B + G - 1) / G;
-    encode_kernel<<<grid, kEncThreads, G * slot_bytes, s>>>(cfg, d_ck, B, G, fix_fillers, d_dn);
+    const int vec = (cfg.Zc % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_ck) | reinterpret_cast<uintptr_t>(d_dn)) % 16 == 0);
+    encode_kernel<<<grid, kEncThreads, G * slot_bytes, s>>>(cfg, d_ck, B, G, fix_fillers, d_dn, vec);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
 }
