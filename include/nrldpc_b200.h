@@ -82,6 +82,21 @@ int nrldpc_decode_minsum(const float *d_llr, int B, int bgn, int Zc, int max_ite
 int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
                               int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters);
 
+/*
+ * Mixed-(bgn, Zc) batch: group g is nrldpc_decode_minsum / nrldpc_encode on B[g] codeblocks of (bgn[g], Zc[g]) with
+ * its own buffers (arrays of ngroups device pointers, host-resident; d_ck / d_info_packed / d_status / d_iters may
+ * be NULL as a whole).  This is what the per-codeblock loops of DLSCHDecode / ULSCH_decoding over several transport
+ * blocks of one slot amount to (py5gphy/nr_pdsch/nr_dlsch_decode.py:83-98, nr_pusch/nr_ulsch_decode.py:86-92; one Zc
+ * per transport block, ldpc_info.get_cbs_info :62-69).  The groups run concurrently on internal streams that fork
+ * from and join back into `stream`: asynchronous to the host, ordered like a single launch on `stream`.
+ */
+int nrldpc_decode_minsum_groups(int ngroups, const float *const *d_llr, const int *B, const int *bgn, const int *Zc,
+                                int max_iter, float alpha, float beta, int early_term, int8_t *const *d_ck,
+                                uint32_t *const *d_info_packed, uint8_t *const *d_status, int32_t *const *d_iters,
+                                void *stream);
+int nrldpc_encode_groups(int ngroups, int8_t *const *d_ck, const int *B, const int *bgn, const int *Zc, int fix_fillers,
+                         int8_t *const *d_dn, void *stream);
+
 /* Launch geometry the hot kernel uses for (bgn, Zc): codeblocks per CTA, threads, dynamic smem bytes. */
 int nrldpc_decode_minsum_geometry(int bgn, int Zc, int *cbs_per_cta, int *threads, int *smem_bytes);
 

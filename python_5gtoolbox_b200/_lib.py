@@ -44,6 +44,8 @@ def _declare(L):
         "nrldpc_decode_minsum": (i, [p, i, i, i, i, f, f, i, p, p, p, p, p]),
         "nrldpc_decode_minsum_host": (i, [p, i, i, i, i, f, f, i, p, p, p, p]),
         "nrldpc_decode_minsum_geometry": (i, [i, i, ip, ip, ip]),
+        "nrldpc_decode_minsum_groups": (i, [i, p, p, p, p, i, f, f, i, p, p, p, p, p]),
+        "nrldpc_encode_groups": (i, [i, p, p, p, p, i, p, p]),
         "nrldpc_decode_csr_host": (i, [p, i, i, i, i, p, p, i, i, d, d, i, p, p, p]),
         "nrldpc_decode_soft_ref_host": (i, [p, i, i, i, i, i, i, d, d, i, p, p, p]),
         "nrldpc_decode_bf_csr_host": (i, [p, i, i, i, p, p, i, p, p, p]),

@@ -160,6 +160,48 @@ static int bf_csr_host(const double *llr, int B, int M, int Nv, const int32_t *r
     return NRLDPC_OK;
 }
 
+// Mixed-(bgn, Zc) batches: every group is one launch; the groups run on a small pool of side streams that fork
+// from and join back into the caller's stream, so that transport blocks of a few codeblocks each (a persistent CTA
+// per codeblock fills one SM) share the GPU instead of running one after the other.
+namespace {
+constexpr int kSideStreams = 8;
+struct SideStreams {
+    cudaStream_t s[kSideStreams] = {};
+    cudaEvent_t fork = nullptr, join[kSideStreams] = {};
+};
+std::mutex g_side_mu;
+std::map<int, SideStreams> g_side;
+
+template <class F>
+int fork_join(cudaStream_t caller, int ngroups, F &&launch_group)
+{
+    if (ngroups <= 0) return NRLDPC_OK;
+    if (ngroups == 1) return launch_group(0, caller);
+    int dev = 0;
+    NRLDPC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    SideStreams &p = g_side[dev];
+    if (!p.fork) {
+        NRLDPC_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+        for (int i = 0; i < kSideStreams; ++i) {
+            NRLDPC_CUDA(cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking));
+            NRLDPC_CUDA(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
+        }
+    }
+    const int used = std::min(ngroups, kSideStreams);
+    NRLDPC_CUDA(cudaEventRecord(p.fork, caller));
+    for (int i = 0; i < used; ++i) NRLDPC_CUDA(cudaStreamWaitEvent(p.s[i], p.fork, 0));
+    int rc = NRLDPC_OK;
+    for (int g = 0; g < ngroups && rc == NRLDPC_OK; ++g) rc = launch_group(g, p.s[g % kSideStreams]);
+    for (int i = 0; i < used; ++i) {  // always join, also after a failed launch
+        cudaEventRecord(p.join[i], p.s[i]);
+        cudaStreamWaitEvent(caller, p.join[i], 0);
+    }
+    return rc;
+}
+}  // namespace
+
+
 }  // namespace nrldpc
 
 using namespace nrldpc;
@@ -228,6 +270,44 @@ int nrldpc_decode_minsum(const float *d_llr, int B, int bgn, int Zc, int max_ite
     if (B < 0 || max_iter < 0 || !d_llr) { set_error("decode_minsum: bad argument"); return NRLDPC_EINVAL; }
     return launch_decode_minsum(*c, d_llr, B, max_iter, alpha, beta, early_term, d_ck, d_info_packed, d_status,
                                 d_iters, (cudaStream_t)stream);
+}
+
+int nrldpc_decode_minsum_groups(int ngroups, const float *const *d_llr, const int *B, const int *bgn, const int *Zc,
+                                int max_iter, float alpha, float beta, int early_term, int8_t *const *d_ck,
+                                uint32_t *const *d_info_packed, uint8_t *const *d_status, int32_t *const *d_iters,
+                                void *stream)
+{
+    if (ngroups < 0 || max_iter < 0 || (ngroups && (!d_llr || !B || !bgn || !Zc))) {
+        set_error("decode_minsum_groups: bad argument");
+        return NRLDPC_EINVAL;
+    }
+    std::vector<const QcCfg *> cfg(ngroups);
+    for (int g = 0; g < ngroups; ++g) {
+        if (!(cfg[g] = get_cfg(bgn[g], Zc[g]))) return NRLDPC_EINVAL;
+        if (B[g] < 0 || (B[g] && !d_llr[g])) { set_error("decode_minsum_groups: bad group %d", g); return NRLDPC_EINVAL; }
+    }
+    return fork_join((cudaStream_t)stream, ngroups, [&](int g, cudaStream_t s) {
+        return launch_decode_minsum(*cfg[g], d_llr[g], B[g], max_iter, alpha, beta, early_term, d_ck ? d_ck[g] : nullptr,
+                                    d_info_packed ? d_info_packed[g] : nullptr, d_status ? d_status[g] : nullptr,
+                                    d_iters ? d_iters[g] : nullptr, s);
+    });
+}
+
+int nrldpc_encode_groups(int ngroups, int8_t *const *d_ck, const int *B, const int *bgn, const int *Zc, int fix_fillers,
+                         int8_t *const *d_dn, void *stream)
+{
+    if (ngroups < 0 || (ngroups && (!d_ck || !d_dn || !B || !bgn || !Zc))) {
+        set_error("encode_groups: bad argument");
+        return NRLDPC_EINVAL;
+    }
+    std::vector<const QcCfg *> cfg(ngroups);
+    for (int g = 0; g < ngroups; ++g) {
+        if (!(cfg[g] = get_cfg(bgn[g], Zc[g]))) return NRLDPC_EINVAL;
+        if (B[g] < 0 || (B[g] && (!d_ck[g] || !d_dn[g]))) { set_error("encode_groups: bad group %d", g); return NRLDPC_EINVAL; }
+    }
+    return fork_join((cudaStream_t)stream, ngroups, [&](int g, cudaStream_t s) {
+        return launch_encode(*cfg[g], d_ck[g], B[g], fix_fillers, d_dn[g], s);
+    });
 }
 
 int nrldpc_decode_minsum_geometry(int bgn, int Zc, int *cbs_per_cta, int *threads, int *smem_bytes)

@@ -124,6 +124,61 @@ def decode_batch(llr, Zc, bgn, L, alpha=1.0, beta=0.0, early_term=True, want_ck=
     return dict(ck=ck, info=info, status=status.astype(bool), iters=iters)
 
 
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
+
+
+def decode_groups(groups, L, alpha=1.0, beta=0.0, early_term=True, want_ck=True, want_info=False):
+    """Mixed-(bgn, Zc) batch on the device: groups = [(llr float32 CUDA [B_g, N_g], Zc_g, bgn_g), ...], e.g. the
+    transport blocks of one slot (one Zc per transport block, py5gphy/ldpc/ldpc_info.py:62-69).  One launch per group,
+    concurrent on the library's side streams, ordered on the current stream.  Returns a list of decode_batch dicts."""
+    import torch
+    n = len(groups)
+    if n == 0:
+        return []
+    dev = groups[0][0].device
+    outs, Bs, bgs, zs = [], [], [], []
+    for llr, Zc, bgn in groups:
+        assert bgn in [1, 2]
+        K, N, Nf, M = dims(bgn, Zc)
+        assert llr.is_cuda and llr.device == dev and llr.dtype == torch.float32 and llr.is_contiguous()
+        assert llr.ndim == 2 and llr.shape[1] == N
+        B = llr.shape[0]
+        outs.append(dict(ck=torch.empty((B, Nf), dtype=torch.int8, device=dev) if want_ck else None,
+                         info=torch.empty((B, (K + 31) // 32), dtype=torch.int32, device=dev) if want_info else None,
+                         status=torch.empty((B,), dtype=torch.uint8, device=dev),
+                         iters=torch.empty((B,), dtype=torch.int32, device=dev)))
+        Bs.append(B), bgs.append(bgn), zs.append(int(Zc))
+    ia = lambda v: (ctypes.c_int * n)(*v)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().nrldpc_decode_minsum_groups(
+            n, _ptr_array([g[0] for g in groups]), ia(Bs), ia(bgs), ia(zs), int(L), float(alpha), float(beta),
+            int(bool(early_term)), _ptr_array([o["ck"] for o in outs]) if want_ck else None,
+            _ptr_array([o["info"] for o in outs]) if want_info else None, _ptr_array([o["status"] for o in outs]),
+            _ptr_array([o["iters"] for o in outs]), _stream_ptr()), "decode_minsum_groups")
+    return outs
+
+
+def encode_groups(groups, fix_fillers=True):
+    """Mixed-(bgn, Zc) encode on the device: groups = [(ck int8 CUDA [B_g, K_g], Zc_g, bgn_g), ...] -> [dn int8 [B_g, N_g]]."""
+    import torch
+    n = len(groups)
+    if n == 0:
+        return []
+    dev = groups[0][0].device
+    dns, Bs, bgs, zs = [], [], [], []
+    for ck, Zc, bgn in groups:
+        K, N, Nf, M = dims(bgn, Zc)
+        assert ck.is_cuda and ck.device == dev and ck.dtype == torch.int8 and ck.is_contiguous() and ck.shape[1] == K
+        dns.append(torch.empty((ck.shape[0], N), dtype=torch.int8, device=dev))
+        Bs.append(ck.shape[0]), bgs.append(bgn), zs.append(int(Zc))
+    ia = lambda v: (ctypes.c_int * n)(*v)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().nrldpc_encode_groups(n, _ptr_array([g[0] for g in groups]), ia(Bs), ia(bgs), ia(zs),
+                                                   int(bool(fix_fillers)), _ptr_array(dns), _stream_ptr()), "encode_groups")
+    return dns
+
+
 def decode_ref_batch(llr, Zc, bgn, L, algo="min-sum", alpha=1.0, beta=0.0, early_term=True, f64=True):
     """The generic (CSR) kernels on the 5G matrix; f64=True reproduces the reference's float64
     arithmetic exactly for 'min-sum'.  NumPy in / out.  Returns (ck int8[B,N'], status bool[B], iters int32[B])."""

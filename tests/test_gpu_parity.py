@@ -349,6 +349,40 @@ def test_decode_headline_roundtrip_device(eng):
     assert int(r3["iters"].max()) == 1 and bool(r3["status"].all())  # punctured bits need one pass
 
 
+def test_mixed_zc_groups_equal_single_launches(eng, oracle):
+    """nrldpc_decode_minsum_groups / nrldpc_encode_groups (one launch per (bgn, Zc) group, concurrent side streams)
+    give bit for bit what one call per group gives -- specialised and table-driven kernels, empty group included."""
+    import torch
+    rng = np.random.default_rng(21)
+    spec = [(1, 384, 9), (2, 352, 5), (1, 208, 7), (2, 28, 11), (1, 12, 40), (2, 176, 3), (1, 72, 6), (2, 384, 4),
+            (1, 2, 33), (1, 320, 0), (2, 96, 8)]
+    cks = [torch.from_numpy(_rand_ck(rng, bgn, Zc, B, fillers=True)).cuda() for bgn, Zc, B in spec]
+    for _ in range(2):
+        ref_dn = [eng.encode_batch(ck.clone(), bgn, Zc) if ck.shape[0] else None for ck, (bgn, Zc, B) in zip(cks, spec)]
+        cks2 = [ck.clone() for ck in cks]
+        dns = eng.encode_groups([(ck, Zc, bgn) for ck, (bgn, Zc, B) in zip(cks2, spec)])
+        for a, b, ck2, ck, (bgn, Zc, B) in zip(ref_dn, dns, cks2, cks, spec):
+            if B:
+                assert torch.equal(a, b), (bgn, Zc)
+                assert int((ck2 == -1).sum()) == int((ck[:, :2 * Zc] == -1).sum())  # fillers fixed in place (:32-35)
+        llrs = []
+        for dn, (bgn, Zc, B) in zip(dns, spec):
+            x = dn.cpu().numpy().astype(np.int8)
+            x[x < 0] = 0
+            llrs.append(torch.from_numpy(_awgn(rng, x, 1.5 if bgn == 1 else 0.5)).cuda())
+        for et in (True, False):
+            out = eng.decode_groups([(l, Zc, bgn) for l, (bgn, Zc, B) in zip(llrs, spec)], 10, 0.8, 0.1, et,
+                                    want_ck=True, want_info=True)
+            torch.cuda.synchronize()
+            for o, l, (bgn, Zc, B) in zip(out, llrs, spec):
+                if not B:
+                    assert o["ck"].shape[0] == 0
+                    continue
+                r = eng.decode_batch(l, Zc, bgn, 10, 0.8, 0.1, et, want_ck=True, want_info=True)
+                for k in ("ck", "info", "status", "iters"):
+                    assert torch.equal(o[k], r[k]), (bgn, Zc, k, et)
+
+
 # ------------------------------------------------------------------ BF / BP / CRC / generic H
 
 def test_bf_vs_oracle_and_golden(eng, oracle, dec_golden):
