@@ -44,6 +44,16 @@ def test_no_device_paths_fail_loudly(so):
         from python_5gtoolbox_b200 import engine, NrLdpcError
         with pytest.raises(NrLdpcError):
             engine.decode_batch(np.zeros((1, 132), np.float32), 2, 1, 4)
+        with pytest.raises(NrLdpcError):
+            engine.decode_bf_batch(np.ones((1, 132)), 2, 1, 4)   # the bit-flipping kernel too
+        assert engine.bind_host_to_device(0) is None            # no device: affinity left alone
+    # argument checks of the mixed-(bgn, Zc) entry points come before any CUDA call
+    one = (ctypes.c_int * 1)(1)
+    bad_zc = (ctypes.c_int * 1)(17)
+    ptrs = (ctypes.c_void_p * 1)(None)
+    assert L.nrldpc_decode_minsum_groups(1, ptrs, one, one, bad_zc, 4, 1.0, 0.0, 1, None, None, None, None, None) == -1
+    assert L.nrldpc_decode_minsum_groups(0, None, None, None, None, 4, 1.0, 0.0, 1, None, None, None, None, None) == 0
+    assert L.nrldpc_encode_groups(-1, None, None, None, None, 1, None, None) == -1
 
 
 def test_csr_matches_oracle(so, oracle):

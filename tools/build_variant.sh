@@ -26,4 +26,4 @@ nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC -Xptxas -v -fmad=false \
   --expt-relaxed-constexpr "$@" -c nrldpc_decode_spec_bg1_384.cu -o $V/spec_$name.o 2> $V/spec_$name.log
 echo "$name: $(grep -E 'Used' $V/spec_$name.log | sed -E 's/.*Used ([0-9]+) registers.*/\1/' | tr '\n' ' ')registers (ET0/B00 ET1/B00 ET0/B01 ET1/B01)"
 nvcc -shared $ARCH -o $V/libnrldpc_$name.so nrldpc_api.o nrldpc_tables.o nrldpc_encode.o nrldpc_decode_qc.o \
-  nrldpc_decode_spec.o $V/spec_$name.o $V/stubs.o nrldpc_generic.o nrldpc_util.o nrldpc_ratematch.o -lcudart
+  nrldpc_decode_spec.o $V/spec_$name.o $V/stubs.o nrldpc_generic.o nrldpc_bf_qc.o nrldpc_util.o nrldpc_ratematch.o -lcudart
