@@ -166,11 +166,270 @@ encode_kernel(const __grid_constant__ QcCfg c, int8_t *__restrict__ ck, int B, i
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Word-parallel encoder for Zc % 32 == 0 (W = Zc/32 words per column-block, no partial word).
+// Thread <-> (codeblock g, word w); the block is 4 parts of kWPart threads and all threads of a part walk the SAME
+// row-block, so the per-edge table reads are warp-uniform and there is no per-edge index arithmetic:
+// every column-block that gets rotated is stored twice back to back (word k and word k + W), hence
+//   word w of (circulant P) @ v  =  funnelshift_r(v2[w + (P >> 5)], v2[w + (P >> 5) + 1], P & 31)
+// with a uniform offset.  The core parity is written in closed form over the four L1 rows
+// (rotations compose: rot(rot(v, a), b) = rot(v, a + b)), so pc1..pc4 are computed by the four parts in parallel
+// from L1 alone (nr_ldpc_encode.py:92-106) and the kernel has 4 barriers.  dn's words are collected in one
+// contiguous array so that the byte <-> bit conversion needs no division on the output side.
+constexpr int kWParts = 4, kWPart = 96, kWThreads = kWParts * kWPart;
+
+__device__ __forceinline__ uint32_t rot2(const uint32_t *v2w, int P)
+{
+    const uint32_t *p = v2w + (P >> 5);
+    return __funnelshift_r(p[0], p[1], P & 31);
+}
+
+// 16 int8 bits (values & 1) -> 16 packed bits
+__device__ __forceinline__ uint32_t pack16(const uint4 &x)
+{
+    const uint32_t a = ((x.x & 0x0f0f0f0fu) | ((x.y << 4) & 0xf0f0f0f0u)) & 0x11111111u;
+    const uint32_t b = ((x.z & 0x0f0f0f0fu) | ((x.w << 4) & 0xf0f0f0f0u)) & 0x11111111u;
+    // byte k of a: bit 0 = byte k of x.x, bit 4 = byte k of x.y; the multiply gathers them in bits 24..31
+    return ((a * 0x01020408u) >> 24) | (((b * 0x01020408u) >> 16) & 0xff00u);
+}
+
+// mask of the bytes equal to 0xFF, one bit per byte
+__device__ __forceinline__ uint32_t ffmask16(const uint4 &x)
+{
+    uint32_t xs[4] = {x.x, x.y, x.z, x.w}, out = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t m = (((xs[q] & 0x7f7f7f7fu) + 0x01010101u) & xs[q] & 0x80808080u) >> 7;
+        out |= ((m * 0x01020408u) >> 24) << (4 * q);
+    }
+    return out;
+}
+
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+constexpr int kWSysMax = 20, kWExtMax = 72;
+
+// Everything the kernel needs, passed by value (constant bank).  An edge descriptor is
+//   (byte offset of word j*2W + (P >> 5) inside the codeblock's doubled column array) << 16 | last-of-row << 5 | (P & 31)
+// so that the address is one LEA.HI and the descriptor itself is the funnel-shift amount (the shift wraps mod 32).
+struct EncWordArgs {
+    int bgn, W, kb, nout, K, N;
+    int G, slot;                 // codeblocks per CTA, words of shared memory per codeblock (without dn's words)
+    uint32_t mKH, mNH, mH;       // floor(2^32 / d) + 1 for d = kb*H, nout*H, H   (H = Zc/16)
+    int s1, s2, s3, s4;          // composed rotations of the closed-form core parity
+    int p3;                      // B(2,3) (BG1) / B(1,1) (BG2)
+    uint16_t nsys[kWParts], next[kWParts];
+    uint32_t sys[kWParts][kWSysMax];   // systematic edges of row-block `part`
+    uint32_t ext[kWParts][kWExtMax];   // edges (all but the last) of row-blocks 4 + part, 8 + part, ...
+};
+
+__device__ __forceinline__ uint32_t rot2d(const uint32_t *v2w, uint32_t d)
+{
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(v2w) + (d >> 16));
+    return __funnelshift_r(p[0], p[1], d);
+}
+
+__global__ void __launch_bounds__(kWThreads)
+encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ ck, int B, int fix_fillers,
+                    int8_t *__restrict__ dn)
+{
+    extern __shared__ uint32_t smem[];
+    __shared__ int any_filler;
+    const int W = a.W, W2 = 2 * W, H = 2 * W, kb = a.kb, nout = a.nout;
+    const int cb0 = blockIdx.x * a.G, g_cnt = min(a.G, B - cb0);
+    // per codeblock slot: D2[kb+4][2W] (systematic + core parity, doubled), L2x[4][2W] (L1 rows, doubled),
+    // FM[kb-2][W] (filler masks, indexed like dn's words); then OUT[G][nout][W]: dn as words, contiguous over the
+    // CTA's codeblocks like dn itself
+    const int oL1 = (kb + 4) * W2, oFM = oL1 + 4 * W2;
+    uint32_t *OUT = smem + a.G * a.slot;
+    const int NH = nout * H;
+    if (threadIdx.x == 0) any_filler = 0;
+    __syncthreads();
+
+    // A. pack: one thread per 16 input bytes; the CTA's codeblocks are contiguous in ck
+    {
+        const int KH = kb * H, total = g_cnt * KH;
+        uint4 *base = reinterpret_cast<uint4 *>(ck + (long long)cb0 * a.K);
+        uint16_t *OUT16 = reinterpret_cast<uint16_t *>(OUT);
+        for (int idx = threadIdx.x; idx < total; idx += kWThreads) {
+            uint4 x = base[idx];
+            const int g = __umulhi((uint32_t)idx, a.mKH), u = idx - g * KH;
+            const int j = __umulhi((uint32_t)u, a.mH);
+            uint32_t fm = 0;
+            if (j >= 2 && ((x.x | x.y | x.z | x.w) & 0x80808080u)) {
+                // bytes equal to -1 at k >= 2Zc are fillers: encoded as 0, reported as -1 (nr_ldpc_encode.py:32-37)
+                fm = ffmask16(x);
+                if (fm) {
+                    uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) xs[q] &= ~(spread4((fm >> (4 * q)) & 0xfu) * 0xffu);
+                    x = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+                    if (fix_fillers) base[idx] = x;
+                    any_filler = 1;
+                }
+            }
+            const uint16_t bits = (uint16_t)pack16(x);
+            // halfword u of the [kb][H] input lands at halfword u + j*H of the doubled array [kb][2][H]
+            uint16_t *cb16 = reinterpret_cast<uint16_t *>(smem + g * a.slot) + u + j * H;
+            cb16[0] = bits;
+            cb16[H] = bits;
+            if (j >= 2) {
+                OUT16[g * NH + u - 2 * H] = bits;
+                reinterpret_cast<uint16_t *>(smem + g * a.slot + oFM)[u - 2 * H] = (uint16_t)fm;
+            }
+        }
+    }
+    __syncthreads();
+
+    const int part = threadIdx.x / kWPart, x = threadIdx.x - part * kWPart;
+    const int g = x / W, w = x - g * W;
+    const bool act = g < g_cnt;
+    uint32_t *cb = smem + g * a.slot;
+    uint32_t *out = OUT + g * nout * W + w;
+    const uint32_t *Dw = cb + w;
+
+    // B. L1[part] = sum over the systematic edges of row-block `part` (:92)
+    if (act) {
+        uint32_t acc = 0;
+        const int n = a.nsys[part];
+        for (int e = 0; e < n; ++e) acc ^= rot2d(Dw, a.sys[part][e]);
+        cb[oL1 + part * W2 + w] = acc;
+        cb[oL1 + part * W2 + W + w] = acc;
+    }
+    __syncthreads();
+
+    // core parity in closed form; part p computes pc_{p+1}.  s1 = roll(L2) as a rotation, s2 = s1 + B(0,0),
+    // s4 = s1 + B(3,0); BG1: pc3 = L1[2] + B(2,3) pc4 (s3 = s4 + p3), BG2: pc3 = L1[1] + B(1,1) pc2 (s3 = s2 + p3)
+    if (act) {
+        const uint32_t *Lw = cb + oL1 + w;
+        const int sh = part == 0 ? a.s1 : part == 1 ? a.s2 : part == 2 ? a.s3 : a.s4;
+        uint32_t acc = rot2(Lw, sh) ^ rot2(Lw + W2, sh) ^ rot2(Lw + 2 * W2, sh) ^ rot2(Lw + 3 * W2, sh);
+        if (part == 1) acc ^= Lw[0];
+        else if (part == 3) acc ^= Lw[3 * W2];
+        else if (part == 2) {
+            if (a.bgn == 1) acc ^= Lw[2 * W2] ^ rot2(Lw + 3 * W2, a.p3);
+            else acc ^= Lw[W2] ^ rot2(Lw, a.p3);
+        }
+        cb[(kb + part) * W2 + w] = acc;
+        cb[(kb + part) * W2 + W + w] = acc;
+        out[(kb - 2 + part) * W] = acc;
+    }
+    __syncthreads();
+
+    // C. extension parity pe = C [ck; pc] (:110-113): every edge of a row-block >= 4 except its last; one flat
+    // edge list per part, the descriptor's bit 5 closes a row-block
+    if (act) {
+        uint32_t acc = 0;
+        uint32_t *o = out + (kb + 2 + part) * W;  // row-block 4 + part -> dn column-block kb - 2 + 4 + part
+        const int n = a.next[part];
+        for (int e = 0; e < n; ++e) {
+            const uint32_t d = a.ext[part][e];
+            acc ^= rot2d(Dw, d);
+            if (d & 32u) {
+                *o = acc;
+                acc = 0;
+                o += kWParts * W;
+            }
+        }
+    }
+    __syncthreads();
+
+    // D. unpack dn: one thread per 16 output bytes, contiguous in dn and in OUT for the CTA's codeblocks
+    {
+        const int total = g_cnt * NH, FH = (kb - 2) * H;
+        uint4 *dst = reinterpret_cast<uint4 *>(dn + (long long)cb0 * a.N);
+        const uint16_t *OUT16 = reinterpret_cast<const uint16_t *>(OUT);
+        const bool fill = any_filler != 0;
+        for (int idx = threadIdx.x; idx < total; idx += kWThreads) {
+            const uint32_t bits = OUT16[idx];
+            uint4 o = make_uint4(spread4(bits & 0xfu), spread4((bits >> 4) & 0xfu), spread4((bits >> 8) & 0xfu),
+                                 spread4(bits >> 12));
+            if (fill) {
+                const int gg = __umulhi((uint32_t)idx, a.mNH), u = idx - gg * NH;
+                if (u < FH) {
+                    const uint32_t fm = reinterpret_cast<const uint16_t *>(smem + gg * a.slot + oFM)[u];
+                    o.x |= spread4(fm & 0xfu) * 0xffu;
+                    o.y |= spread4((fm >> 4) & 0xfu) * 0xffu;
+                    o.z |= spread4((fm >> 8) & 0xfu) * 0xffu;
+                    o.w |= spread4(fm >> 12) * 0xffu;
+                }
+            }
+            dst[idx] = o;
+        }
+    }
+}
+
+int find_edge_host(const QcCfg &c, int i, int j)
+{
+    for (int e = c.rowptr[i]; e < c.rowptr[i + 1]; ++e)
+        if ((int)(c.edge[e] & 0xff) == j) return (int)(c.edge[e] >> 8);
+    return 0;
+}
+
+int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s)
+{
+    const int W = c.tiles, H = 2 * W, kb = c.kb, nout = c.ncols - 2, Zc = c.Zc;
+    EncWordArgs a = {};
+    a.bgn = c.bgn; a.W = W; a.kb = kb; a.nout = nout; a.K = c.K; a.N = c.N;
+    a.G = kWPart / W;
+    int slot = (kb + 8) * 2 * W + (kb - 2) * W;
+    slot += ((W - slot) % 32 + 32) % 32;  // slot = W (mod 32): thread (g, w) falls in bank (g W + w) mod 32
+    a.slot = slot;
+    auto magic = [](uint32_t d) { return (uint32_t)((1ull << 32) / d) + 1u; };
+    a.mKH = magic(kb * H);
+    a.mNH = magic(nout * H);
+    a.mH = magic(H);
+    const int sroll = find_edge_host(c, c.bgn == 1 ? 1 : 2, kb);
+    const int p00 = find_edge_host(c, 0, kb), p30 = find_edge_host(c, 3, kb);
+    a.p3 = c.bgn == 1 ? find_edge_host(c, 2, kb + 3) : find_edge_host(c, 1, kb + 1);
+    a.s1 = (Zc - sroll) % Zc;
+    a.s2 = (a.s1 + p00) % Zc;
+    a.s4 = (a.s1 + p30) % Zc;
+    a.s3 = ((c.bgn == 1 ? a.s4 : a.s2) + a.p3) % Zc;
+    auto desc = [&](uint32_t ed, int last) {
+        const int j = ed & 0xff, P = ed >> 8;
+        return (uint32_t)((j * 2 * W + (P >> 5)) * 4) << 16 | (uint32_t)last << 5 | (uint32_t)(P & 31);
+    };
+    for (int p = 0; p < kWParts; ++p) {
+        int n = 0;
+        for (int e = c.rowptr[p]; e < c.rowptr[p + 1]; ++e)
+            if ((int)(c.edge[e] & 0xff) < kb) {
+                if (n >= kWSysMax) { set_error("encode: systematic edge list overflow"); return NRLDPC_EINVAL; }
+                a.sys[p][n++] = desc(c.edge[e], 0);
+            }
+        a.nsys[p] = (uint16_t)n;
+        n = 0;
+        for (int i = 4 + p; i < c.nrows; i += kWParts) {
+            const int e1 = c.rowptr[i + 1] - 1;
+            for (int e = c.rowptr[i]; e < e1; ++e) {
+                if (n >= kWExtMax) { set_error("encode: extension edge list overflow"); return NRLDPC_EINVAL; }
+                a.ext[p][n++] = desc(c.edge[e], e == e1 - 1);
+            }
+        }
+        a.next[p] = (uint16_t)n;
+    }
+    const int smem_bytes = a.G * (slot + nout * W) * 4;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    NRLDPC_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_done[dev]) {
+        NRLDPC_CUDA(cudaFuncSetAttribute(encode_words_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        attr_done[dev] = true;
+    }
+    const int grid = (B + a.G - 1) / a.G;
+    encode_words_kernel<<<grid, kWThreads, smem_bytes, s>>>(a, d_ck, B, fix_fillers, d_dn);
+    NRLDPC_CUDA(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
 }  // namespace
 
 int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s)
 {
     if (B <= 0) return NRLDPC_OK;
+    if (cfg.Zc % 32 == 0 && (reinterpret_cast<uintptr_t>(d_ck) | reinterpret_cast<uintptr_t>(d_dn)) % 16 == 0)
+        return launch_encode_words(cfg, d_ck, B, fix_fillers, d_dn, s);
     const int Wp = cfg.tiles + 1;
     const int slot_bytes = (cfg.ncols * Wp + cfg.kb * cfg.tiles + 5 * Wp) * 4;
     // enough codeblocks per CTA to give 256 threads work, bounded by 48 KB of static-limit shared memory
