@@ -165,7 +165,8 @@ def test_decode_all_lifting_sizes_vs_oracle(eng, oracle, bgn):
 
 
 @pytest.mark.parametrize("bgn,Zc", [(1, 384), (2, 384), (1, 352), (2, 352), (1, 320), (2, 320), (1, 288), (2, 288),
-                                    (1, 208), (2, 208), (1, 176), (2, 176)])
+                                    (1, 256), (2, 256), (1, 240), (2, 240), (1, 224), (2, 224),
+                                    (1, 208), (2, 208), (1, 192), (2, 192), (1, 176), (2, 176)])
 def test_decode_headline_spec_kernel_vs_oracle(eng, oracle, bgn, Zc):
     """These (bgn, Zc) go through the compile-time specialised kernels (nrldpc_decode_spec.cuh): bit-exact
     against the fp32 restatement for NMS / OMS / mixed / plain min-sum, with and without early
