@@ -3,7 +3,7 @@
 
 namespace nrldpc {
 
-#define NRLDPC_SPEC_LIST(X) X(1, 384) X(2, 384) X(1, 352) X(2, 352) X(1, 320) X(2, 320) X(1, 288) X(2, 288) X(1, 256) X(2, 256) X(1, 240) X(2, 240) X(1, 224) X(2, 224) X(1, 208) X(2, 208) X(1, 192) X(2, 192) X(1, 176) X(2, 176)
+#define NRLDPC_SPEC_LIST(X) X(1, 384) X(2, 384) X(1, 352) X(2, 352) X(1, 320) X(2, 320) X(1, 288) X(2, 288) X(1, 256) X(2, 256) X(1, 240) X(2, 240) X(1, 224) X(2, 224) X(1, 208) X(2, 208) X(1, 192) X(2, 192) X(1, 176) X(2, 176) X(1, 160) X(2, 160) X(1, 144) X(2, 144)
 
 #define NRLDPC_DECLARE(BGN, ZC)                                                                 \
     int launch_decode_spec_##BGN##_##ZC(const DecArgs &a, int early_term, cudaStream_t s);      \

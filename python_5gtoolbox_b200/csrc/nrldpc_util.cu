@@ -36,8 +36,12 @@ __global__ void random_bits_kernel(int8_t *bits, long long rows, long long cols,
 {
     const long long bpr = (cols + 127) / 128, nblk = rows * bpr;  // one Philox block = 128 bits
     const bool vec8 = (cols % 8 == 0) && (reinterpret_cast<uintptr_t>(bits) % 8 == 0);
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nblk; t += (long long)gridDim.x * blockDim.x) {
-        const long long row = t / bpr, blk = t - row * bpr;
+    // (row, blk) of block t advance incrementally: one 64-bit division per thread instead of one per block
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long srow = stride / bpr, sblk = stride - srow * bpr;
+    long long row = t0 / bpr, blk = t0 - row * bpr;
+    for (long long t = t0; t < nblk; t += stride, row += srow, blk += sblk) {
+        if (blk >= bpr) { blk -= bpr; ++row; }
         const uint4 x = philox_at(seed, ctr0 + (unsigned long long)((first_id + row * id_stride) * bpr + blk));
         const uint32_t w[4] = {x.x, x.y, x.z, x.w};
         const long long base = blk * 128;
@@ -64,8 +68,11 @@ __global__ void awgn_llr_kernel(const int8_t *__restrict__ dn, long long rows, l
 {
     const long long bpr = (cols + 3) / 4, nblk = rows * bpr;  // one Philox block = 4 normals
     const bool vec4 = (cols % 4 == 0) && (reinterpret_cast<uintptr_t>(dn) % 4 == 0) && (reinterpret_cast<uintptr_t>(llr) % 16 == 0);
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nblk; t += (long long)gridDim.x * blockDim.x) {
-        const long long row = t / bpr, blk = t - row * bpr;
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long srow = stride / bpr, sblk = stride - srow * bpr;
+    long long row = t0 / bpr, blk = t0 - row * bpr;
+    for (long long t = t0; t < nblk; t += stride, row += srow, blk += sblk) {
+        if (blk >= bpr) { blk -= bpr; ++row; }
         const uint4 x = philox_at(seed ^ 0x9E3779B97F4A7C15ull, ctr0 + (unsigned long long)((first_id + row * id_stride) * bpr + blk));
         // Box-Muller on two uniform pairs
         const float u0 = ((x.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((x.y >> 8) + 0.5f) * (1.0f / 16777216.0f);

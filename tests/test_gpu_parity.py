@@ -166,7 +166,8 @@ def test_decode_all_lifting_sizes_vs_oracle(eng, oracle, bgn):
 
 @pytest.mark.parametrize("bgn,Zc", [(1, 384), (2, 384), (1, 352), (2, 352), (1, 320), (2, 320), (1, 288), (2, 288),
                                     (1, 256), (2, 256), (1, 240), (2, 240), (1, 224), (2, 224),
-                                    (1, 208), (2, 208), (1, 192), (2, 192), (1, 176), (2, 176)])
+                                    (1, 208), (2, 208), (1, 192), (2, 192), (1, 176), (2, 176), (1, 160), (2, 160),
+                                    (1, 144), (2, 144)])
 def test_decode_headline_spec_kernel_vs_oracle(eng, oracle, bgn, Zc):
     """These (bgn, Zc) go through the compile-time specialised kernels (nrldpc_decode_spec.cuh): bit-exact
     against the fp32 restatement for NMS / OMS / mixed / plain min-sum, with and without early
@@ -580,3 +581,26 @@ def test_headline_size_properties(eng):
     r3 = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, False)
     r4 = eng.decode_batch(llr2, Zc, bgn, 10, 0.8, 0.0, False)
     assert torch.equal(r4["ck"], r3["ck"] ^ fullb) and torch.equal(r4["status"], r3["status"])
+
+
+@pytest.mark.gpu
+def test_philox_rows_equal_flat_streams(eng):
+    """Monte-Carlo helpers: row j of nrldpc_random_bits_rows / nrldpc_awgn_llr_rows (codeblock id = first_id + j * stride)
+    is the flat generator at Philox offset id * blocks_per_row, for a batch large enough that every thread walks many
+    (row, block) pairs -- the random stream of a codeblock depends on its global id only, not on the sharding."""
+    import torch
+    from python_5gtoolbox_b200 import _lib
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    for rows, cols, first, stride in [(3000, 25344, 5, 3), (4097, 1320, 0, 1), (7, 100, 11, 8)]:
+        bits = torch.empty((rows, cols), dtype=torch.int8, device="cuda")
+        _lib.check(L.nrldpc_random_bits_rows(bits.data_ptr(), rows, cols, 77, first, stride, s), "bits")
+        llr = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+        _lib.check(L.nrldpc_awgn_llr_rows(bits.data_ptr(), rows, cols, 1.25, 78, first, stride, llr.data_ptr(), s), "awgn")
+        for j in sorted({0, 1, rows // 2, rows - 2, rows - 1}):
+            cid = first + j * stride
+            b1 = eng.random_bits(1, cols, seed=77, device="cuda", offset=cid * ((cols + 127) // 128))
+            assert torch.equal(b1[0], bits[j]), (rows, cols, j)
+            l1 = eng.awgn_llr(bits[j:j + 1].contiguous(), 1.25, seed=78, offset=cid * ((cols + 3) // 4))
+            assert torch.equal(l1[0], llr[j]), (rows, cols, j)
+        assert int(bits.min()) == 0 and int(bits.max()) == 1 and abs(float(bits.float().mean()) - 0.5) < 0.01
