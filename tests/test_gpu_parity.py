@@ -603,4 +603,6 @@ def test_philox_rows_equal_flat_streams(eng):
             assert torch.equal(b1[0], bits[j]), (rows, cols, j)
             l1 = eng.awgn_llr(bits[j:j + 1].contiguous(), 1.25, seed=78, offset=cid * ((cols + 3) // 4))
             assert torch.equal(l1[0], llr[j]), (rows, cols, j)
-        assert int(bits.min()) == 0 and int(bits.max()) == 1 and abs(float(bits.float().mean()) - 0.5) < 0.01
+        assert int(bits.min()) == 0 and int(bits.max()) == 1
+        if rows * cols > 1_000_000:
+            assert abs(float(bits.float().mean()) - 0.5) < 0.005
