@@ -13,6 +13,7 @@ struct DecArgs {
     uint32_t *info;
     uint8_t *status;
     int32_t *iters;
+    int *work = nullptr;  // early-termination kernels: zeroed ticket counter of the dynamic codeblock queue (or null: static stride)
 };
 
 constexpr uint32_t kInfBits = 0x7f800000u;

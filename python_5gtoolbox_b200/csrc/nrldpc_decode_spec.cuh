@@ -700,6 +700,7 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
 {
     extern __shared__ __align__(16) char smem[];
     __shared__ int s_flag[2];
+    __shared__ int s_next;
     constexpr int NT = C::nwarps * 32, ZC = C::ZC;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __reduce_min_sync(0xffffffffu, tid >> 5);  // warp-uniform (REDUX writes a uniform register)
@@ -738,10 +739,19 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     // HBM latency is exposed at a codeblock boundary.
     const bool pf = tid == 0 && (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0;  // bulk prefetch needs 16-byte alignment
     if (pf) prefetch_l2(a.llr + (size_t)blockIdx.x * C::N, C::N * 4);
+    // With early termination the codeblocks take different numbers of iterations, so the CTAs draw them from a
+    // ticket counter (a.work) instead of a fixed stride: the first one is blockIdx.x, every further one
+    // gridDim.x + ticket.  Thread 0 takes the ticket of the NEXT codeblock at the top (its latency hides behind the
+    // state initialisation), prefetches that codeblock's LLRs and publishes the index before the first barrier.
+    const bool dyn = ET && a.work != nullptr;
     for (int cb = blockIdx.x; cb < a.B; cb += gridDim.x) {
+        int nx = 0;
+        if (ET) { if (dyn && tid == 0) nx = (int)gridDim.x + atomicAdd(a.work, 1); }
         th.llr = a.llr + (size_t)cb * C::N + th.r;
 #ifndef NRLDPC_EXP_NO_PF
-        if (pf && cb + (int)gridDim.x < a.B) prefetch_l2(a.llr + (size_t)(cb + gridDim.x) * C::N, C::N * 4);
+        if (!dyn) {
+            if (pf && cb + (int)gridDim.x < a.B) prefetch_l2(a.llr + (size_t)(cb + gridDim.x) * C::N, C::N * 4);
+        }
 
 #endif
 
@@ -765,7 +775,14 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
                 if (th.tile == 0) dst[ZC] = v;
             }
         }
+        if (ET) {
+            if (dyn && tid == 0) {
+                s_next = nx;
+                if (pf && nx < a.B) prefetch_l2(a.llr + (size_t)nx * C::N, C::N * 4);
+            }
+        }
         __syncthreads();
+        if (ET) { if (dyn) nx = s_next; }
 
         bool et_done = false;
         int it = 0;
@@ -843,6 +860,7 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
         }
 #endif
         __syncthreads();  // the state is re-initialised for the next codeblock
+        if (ET) { if (dyn) cb = nx - (int)gridDim.x; }  // the loop adds the stride back
     }
 }
 
@@ -859,8 +877,18 @@ int launch_spec(const DecArgs &a, int early_term, cudaStream_t s)
             fprintf(stderr, "nrldpc: decode_spec<%d,%d> threads=%d smem=%d ctas/SM wanted=%d resident=%d\n", C::bgn, C::ZC,
                     C::nwarps * 32, C::smem_bytes, C::ctas, nb);
         }
-        kern<<<std::min(a.B, C::ctas * num_sms()), C::nwarps * 32, C::smem_bytes, s>>>(a);
+        const int grid = std::min(a.B, C::ctas * num_sms());
+        DecArgs b = a;
+        // dynamic codeblock queue of the early-termination kernels: worth a stream-ordered 4-byte allocation + memset
+        // once every CTA decodes several codeblocks (NRLDPC_STATIC_QUEUE=1: fixed stride, for A/B timing)
+        static const bool static_queue = getenv("NRLDPC_STATIC_QUEUE") != nullptr;
+        if (early_term && a.B >= 2 * grid && !static_queue) {
+            NRLDPC_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&b.work), sizeof(int), s));
+            NRLDPC_CUDA(cudaMemsetAsync(b.work, 0, sizeof(int), s));
+        }
+        kern<<<grid, C::nwarps * 32, C::smem_bytes, s>>>(b);
         NRLDPC_CUDA(cudaGetLastError());
+        if (b.work) NRLDPC_CUDA(cudaFreeAsync(b.work, s));
         return NRLDPC_OK;
     };
     if (a.beta == 0.f) return early_term ? launch(decode_spec_kernel<C, true, true>) : launch(decode_spec_kernel<C, false, true>);
