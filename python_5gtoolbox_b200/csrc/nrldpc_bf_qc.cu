@@ -154,15 +154,17 @@ bf_qc_kernel(const __grid_constant__ QcCfg cfg, const T *__restrict__ llr, int B
 // twice back to back, so a rotation is 2 LDS + 1 SHF without wrap arithmetic.  Two edges enter the bit-plane
 // counters through one full adder (2 LOP3) before the ripple.  A CTA holds G = 96/W codeblocks, each with its
 // own maximum, zero-syndrome test and iteration count; a thread flips the words it evaluated itself.
-constexpr int kBwParts = 8, kBwPart = 96, kBwThreads = kBwParts * kBwPart, kBwList = 64;
+constexpr int kBwParts = 8, kBwPart = 96, kBwThreads = kBwParts * kBwPart, kBwList = 64, kBwIds = 12;
 
 struct BfWordArgs {
     int W, Zc, ncols, nrows, ncore, N, Nfull;
     int G, slot;  // codeblocks per CTA, words of shared memory per codeblock
     uint32_t mNW, mW;  // floor(2^32 / d) + 1 for d = (ncols - 2) W and d = W
     uint16_t nrow[kBwParts], ncol[kBwParts];
-    uint32_t rowl[kBwParts][kBwList];  // core-column edges of row-blocks p, p + 8, ...  (offsets into CK2)
-    uint32_t coll[kBwParts][kBwList];  // edges of core column-blocks p, p + 8, ...      (offsets into SW2)
+    uint8_t nrid[kBwParts], ncid[kBwParts];            // row-blocks / core column-blocks of a part (balanced by edge count)
+    uint8_t rowid[kBwParts][kBwIds], colid[kBwParts][kBwIds];
+    uint32_t rowl[kBwParts][kBwList];  // core-column edges of the part's row-blocks, in rowid order (offsets into CK2)
+    uint32_t coll[kBwParts][kBwList];  // edges of the part's core column-blocks, in colid order  (offsets into SW2)
 };
 
 __device__ __forceinline__ uint32_t bw_rot(const uint32_t *v2w, uint32_t d)
@@ -227,17 +229,17 @@ bf_words_kernel(const __grid_constant__ BfWordArgs a, const T *__restrict__ llr,
         // :47 S = H ck mod 2 for the row-blocks of this part
         if (act) {
             uint32_t acc = 0, any = 0;
-            int i = part;
+            int k = 0;
             for (int e = 0; e < nr; ++e) {
                 const uint32_t d = a.rowl[part][e];
                 acc ^= bw_rot(CKw, d);
                 if (d & 32u) {
+                    const int i = a.rowid[part][k++];
                     if (i >= 4) acc ^= cb[oCKX + (i - 4) * W + w];  // the row-block's own degree-1 column, shift 0
                     cb[oSW + i * W2 + w] = acc;
                     cb[oSW + i * W2 + W + w] = acc;
                     any |= acc;
                     acc = 0;
-                    i += kBwParts;
                 }
             }
             if (any) s_any[g] = 1;
@@ -248,7 +250,7 @@ bf_words_kernel(const __grid_constant__ BfWordArgs a, const T *__restrict__ llr,
         // :61-62 En of the words of this part's column-blocks, maximum per codeblock
         int mymax = -128;
         if (act) {
-            int j = part;
+            int k = 0;
             uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
             int deg = 0;
             for (int e = 0; e < nc; ++e) {
@@ -283,12 +285,12 @@ bf_words_kernel(const __grid_constant__ BfWordArgs a, const T *__restrict__ llr,
                 m = mask & c1; if (m) { mask = m; u |= 2; }
                 m = mask & c0; if (m) { mask = m; u |= 1; }
                 const int en = 2 * u - deg;
+                const int j = a.colid[part][k++];
                 cb[oMK + j * W + w] = mask;
                 EN[j * W + w] = (int8_t)en;
                 mymax = max(mymax, en);
                 c0 = c1 = c2 = c3 = c4 = 0;
                 deg = 0;
-                j += kBwParts;
             }
             // degree-1 extension column-blocks ncore + k, k = part, part + 8, ...: En = +1 where the row-block's check fails
             for (int k = part; k < next; k += kBwParts) {
@@ -309,12 +311,14 @@ bf_words_kernel(const __grid_constant__ BfWordArgs a, const T *__restrict__ llr,
         // :67-70 flip every bit whose metric equals the codeblock's maximum (each thread: the words it evaluated)
         if (act) {
             const int mx = s_max[g];
-            for (int j = part; j < ncore; j += kBwParts)
+            for (int k = 0; k < a.ncid[part]; ++k) {
+                const int j = a.colid[part][k];
                 if (EN[j * W + w] == mx) {
                     const uint32_t v = cb[j * W2 + w] ^ cb[oMK + j * W + w];
                     cb[j * W2 + w] = v;
                     cb[j * W2 + W + w] = v;
                 }
+            }
             for (int k = part; k < next; k += kBwParts)
                 if (EN[(ncore + k) * W + w] == mx) cb[oCKX + k * W + w] ^= cb[oMK + (ncore + k) * W + w];
         }
@@ -354,37 +358,49 @@ int launch_bf_words(const QcCfg &c, const void *d_llr, int is_f64, int B, int ma
     a.slot = slot;
     a.mNW = (uint32_t)((1ull << 32) / (uint32_t)((c.ncols - 2) * W)) + 1u;
     a.mW = (uint32_t)((1ull << 32) / (uint32_t)W) + 1u;
-    for (int p = 0; p < kBwParts; ++p) {
-        int n = 0;
-        for (int i = p; i < c.nrows; i += kBwParts) {
+    {   // row-blocks and core column-blocks go to the least loaded part, heaviest first (round robin would give the
+        // part that owns BG1 column-blocks 0 / row-blocks 0-3 1.6x / 1.3x the average number of edges)
+        int load[kBwParts] = {}, order[kMaxRows];
+        int deg[kMaxRows];
+        for (int i = 0; i < c.nrows; ++i) { deg[i] = c.rowptr[i + 1] - c.rowptr[i] - (i >= 4 ? 1 : 0); order[i] = i; }
+        std::stable_sort(order, order + c.nrows, [&](int x, int y) { return deg[x] > deg[y]; });
+        for (int t = 0; t < c.nrows; ++t) {
+            const int i = order[t], p = (int)(std::min_element(load, load + kBwParts) - load);
+            if (a.nrid[p] >= kBwIds || a.nrow[p] + deg[i] > kBwList) return NRLDPC_OK;  // not handled: bf_qc_kernel
+            load[p] += deg[i] + 2;
+            a.rowid[p][a.nrid[p]++] = (uint8_t)i;
             const int e1 = c.rowptr[i + 1] - (i >= 4 ? 1 : 0);  // rows >= 4: the last edge is the degree-1 column
             for (int e = c.rowptr[i]; e < e1; ++e) {
-                if (n >= kBwList) return NRLDPC_OK;  // not handled: the caller falls back to bf_qc_kernel
                 const int j = c.edge[e] & 0xff, P = c.edge[e] >> 8;
                 if (j >= c.ncore) return NRLDPC_OK;
-                a.rowl[p][n++] = (uint32_t)((j * 2 * W + (P >> 5)) * 4) << 16 | (uint32_t)(e == e1 - 1) << 5 | (uint32_t)(P & 31);
+                a.rowl[p][a.nrow[p]++] = (uint32_t)((j * 2 * W + (P >> 5)) * 4) << 16 | (uint32_t)(e == e1 - 1) << 5 | (uint32_t)(P & 31);
             }
         }
-        a.nrow[p] = (uint16_t)n;
-        n = 0;
-        for (int j = p; j < c.ncore; j += kBwParts) {
+        std::fill(load, load + kBwParts, 0);
+        for (int j = 0; j < c.ncore; ++j) { deg[j] = c.colptr[j + 1] - c.colptr[j]; order[j] = j; }
+        std::stable_sort(order, order + c.ncore, [&](int x, int y) { return deg[x] > deg[y]; });
+        for (int t = 0; t < c.ncore; ++t) {
+            const int j = order[t], p = (int)(std::min_element(load, load + kBwParts) - load);
+            if (a.ncid[p] >= kBwIds || a.ncol[p] + deg[j] > kBwList) return NRLDPC_OK;
+            load[p] += deg[j] + 3;
+            a.colid[p][a.ncid[p]++] = (uint8_t)j;
             const int q1 = c.colptr[j + 1];
             for (int q = c.colptr[j]; q < q1; ++q) {
-                if (n >= kBwList) return NRLDPC_OK;
                 const int i = c.centry[q] & 0x3f, back = c.centry[q] >> 16;
-                a.coll[p][n++] = (uint32_t)(((c.nrows > 0 ? i : 0) * 2 * W + (back >> 5)) * 4) << 16 | (uint32_t)(q == q1 - 1) << 5 | (uint32_t)(back & 31);
+                a.coll[p][a.ncol[p]++] = (uint32_t)((i * 2 * W + (back >> 5)) * 4) << 16 | (uint32_t)(q == q1 - 1) << 5 | (uint32_t)(back & 31);
             }
         }
-        a.ncol[p] = (uint16_t)n;
     }
     const int smem_bytes = a.G * slot * 4;
     if (smem_bytes > 200 * 1024) return NRLDPC_OK;
     *handled = true;
     if (is_f64) {
         NRLDPC_CUDA(cudaFuncSetAttribute(bf_words_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        NRLDPC_CUDA(cudaFuncSetAttribute(bf_words_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         bf_words_kernel<double><<<(B + a.G - 1) / a.G, kBwThreads, smem_bytes, s>>>(a, (const double *)d_llr, B, max_iter, d_ck, d_status, d_iters);
     } else {
         NRLDPC_CUDA(cudaFuncSetAttribute(bf_words_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        NRLDPC_CUDA(cudaFuncSetAttribute(bf_words_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         bf_words_kernel<float><<<(B + a.G - 1) / a.G, kBwThreads, smem_bytes, s>>>(a, (const float *)d_llr, B, max_iter, d_ck, d_status, d_iters);
     }
     NRLDPC_CUDA(cudaGetLastError());
