@@ -174,7 +174,7 @@ __device__ __forceinline__ uint32_t bw_rot(const uint32_t *v2w, uint32_t d)
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBwThreads)
+__global__ void __launch_bounds__(kBwThreads, 2)
 bf_words_kernel(const __grid_constant__ BfWordArgs a, const T *__restrict__ llr, int B, int max_iter,
                 int8_t *__restrict__ ck_out, uint8_t *__restrict__ status, int32_t *__restrict__ iters)
 {
