@@ -13,8 +13,12 @@ struct DecArgs {
     uint32_t *info;
     uint8_t *status;
     int32_t *iters;
-    int *work = nullptr;  // early-termination kernels: zeroed ticket counter of the dynamic codeblock queue (or null: static stride)
+    int *work = nullptr;  // early-termination kernels: {ticket counter, CTAs done} slot of the dynamic codeblock queue, both zero
+                          // at launch and zeroed again by the last CTA (or null: static stride)
 };
+
+// next slot of the current device's ring of queue slots (nrldpc_decode_spec.cu)
+int decode_queue_slot(int **slot);
 
 constexpr uint32_t kInfBits = 0x7f800000u;
 

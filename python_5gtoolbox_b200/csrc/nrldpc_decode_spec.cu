@@ -1,4 +1,6 @@
 // nrldpc_decode_spec.cu -- dispatch to the compile-time specialised decoder kernels (nrldpc_decode_spec.cuh).
+#include <mutex>
+
 #include "nrldpc_decode.cuh"
 
 namespace nrldpc {
@@ -17,6 +19,27 @@ int launch_decode_spec(int bgn, int Zc, const DecArgs &a, int early_term, cudaSt
     NRLDPC_SPEC_LIST(NRLDPC_CASE)
 #undef NRLDPC_CASE
     *handled = false;
+    return NRLDPC_OK;
+}
+
+// Ring of {ticket, done} slots per device for the dynamic codeblock queue of the early-termination kernels.  A slot is
+// zero whenever no kernel is using it (the last CTA of a launch zeroes it), so a launch only draws the next index;
+// two launches share a slot only if kSlots launches are in flight at once.
+int decode_queue_slot(int **slot)
+{
+    constexpr int kSlots = 4096, kMaxDev = 64;
+    static std::mutex mu;
+    static int *ring[kMaxDev] = {};
+    static unsigned next[kMaxDev] = {};
+    int dev = 0;
+    NRLDPC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) { *slot = nullptr; return NRLDPC_OK; }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ring[dev]) {
+        NRLDPC_CUDA(cudaMalloc(reinterpret_cast<void **>(&ring[dev]), kSlots * 2 * sizeof(int)));
+        NRLDPC_CUDA(cudaMemset(ring[dev], 0, kSlots * 2 * sizeof(int)));
+    }
+    *slot = ring[dev] + 2 * (next[dev]++ % kSlots);
     return NRLDPC_OK;
 }
 

@@ -862,6 +862,14 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
         __syncthreads();  // the state is re-initialised for the next codeblock
         if (ET) { if (dyn) cb = nx - (int)gridDim.x; }  // the loop adds the stride back
     }
+    if (ET) {
+        // the last CTA to leave puts the queue slot back to zero for the next launch that draws it (every CTA has
+        // taken its last ticket before it counts itself out)
+        if (dyn && tid == 0) {
+            __threadfence();
+            if (atomicAdd(a.work + 1, 1) == (int)gridDim.x - 1) { a.work[0] = 0; a.work[1] = 0; }
+        }
+    }
 }
 
 template <class C>
@@ -879,16 +887,15 @@ int launch_spec(const DecArgs &a, int early_term, cudaStream_t s)
         }
         const int grid = std::min(a.B, C::ctas * num_sms());
         DecArgs b = a;
-        // dynamic codeblock queue of the early-termination kernels: worth a stream-ordered 4-byte allocation + memset
-        // once every CTA decodes several codeblocks (NRLDPC_STATIC_QUEUE=1: fixed stride, for A/B timing)
+        // dynamic codeblock queue of the early-termination kernels, once every CTA decodes several codeblocks: a
+        // {ticket, CTAs done} slot of a per-device ring that the kernel itself returns to zero (no allocation or memset on
+        // the launch path; NRLDPC_STATIC_QUEUE=1: fixed stride, for A/B timing)
         static const bool static_queue = getenv("NRLDPC_STATIC_QUEUE") != nullptr;
         if (early_term && a.B >= 2 * grid && !static_queue) {
-            NRLDPC_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&b.work), sizeof(int), s));
-            NRLDPC_CUDA(cudaMemsetAsync(b.work, 0, sizeof(int), s));
+            if (int rc = decode_queue_slot(&b.work)) return rc;
         }
         kern<<<grid, C::nwarps * 32, C::smem_bytes, s>>>(b);
         NRLDPC_CUDA(cudaGetLastError());
-        if (b.work) NRLDPC_CUDA(cudaFreeAsync(b.work, s));
         return NRLDPC_OK;
     };
     if (a.beta == 0.f) return early_term ? launch(decode_spec_kernel<C, true, true>) : launch(decode_spec_kernel<C, false, true>);
