@@ -1,6 +1,8 @@
 // nrldpc_util.cu -- device-side Monte-Carlo helpers: Philox bits, BPSK/AWGN LLRs, error counters.
 // Replaces the per-codeblock host loop of for_test_5g_ldpc_encoder (py5gphy/ldpc/nr_ldpc_decode.py:247-257)
 // and the np.array_equal bookkeeping of scripts/internal/sim_ldpc_internal.py:61-62.
+#include <algorithm>
+
 #include "nrldpc_common.cuh"
 
 namespace nrldpc {
@@ -164,7 +166,7 @@ __global__ void crc_kernel(const int8_t *__restrict__ in, int B, int A, int L, u
 // (square-and-multiply in GF(2)[x]/P, ~40 L-step products) and the partial remainders are XOR-reduced.
 constexpr int kCrcBlockThreads = 256;  // long blocks; medium blocks (a codeblock's payload) use 64: fewer x^s products
 
-__device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b, int L, uint32_t poly, uint32_t mask)
+__host__ __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b, int L, uint32_t poly, uint32_t mask)
 {
     uint32_t res = 0;
     for (int i = L - 1; i >= 0; --i) {
@@ -176,10 +178,14 @@ __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b, int L, ui
     return res;
 }
 
+// x^(A - k1(t)) mod P of every thread's chunk, computed on the host per launch (one product per thread in the kernel
+// instead of a square-and-multiply chain of ~40)
+struct CrcPow { uint32_t p[kCrcBlockThreads]; };
+
 template <int T>
 __global__ void __launch_bounds__(T)
-crc_block_kernel(const int8_t *__restrict__ in, int A, int L, uint32_t poly, int mode, int8_t *__restrict__ out,
-                 uint8_t *__restrict__ err)
+crc_block_kernel(const __grid_constant__ CrcPow pw, const int8_t *__restrict__ in, int A, int L, uint32_t poly, int mode,
+                 int8_t *__restrict__ out, uint8_t *__restrict__ err)
 {
     constexpr int kCrcBlockThreads = T;
     __shared__ uint32_t s_part[kCrcBlockThreads / 32];
@@ -195,15 +201,7 @@ crc_block_kernel(const int8_t *__restrict__ in, int A, int L, uint32_t poly, int
         rem = (rem << 1) & mask;
         if (fb) rem ^= poly;
     }
-    if (rem) {  // times x^(A - k1) mod P
-        uint32_t e = (uint32_t)(A - k1), base = 2u, acc = 1u;
-        while (e) {
-            if (e & 1u) acc = gf2_mulmod(acc, base, L, poly, mask);
-            base = gf2_mulmod(base, base, L, poly, mask);
-            e >>= 1;
-        }
-        rem = gf2_mulmod(rem, acc, L, poly, mask);
-    }
+    if (rem && k1 < A) rem = gf2_mulmod(rem, pw.p[tid], L, poly, mask);  // times x^(A - k1) mod P
 #pragma unroll
     for (int o = 16; o; o >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, o);
     if (lane == 0) s_part[tid >> 5] = rem;
@@ -300,6 +298,37 @@ static int crc_poly(int poly_id, int *L, uint32_t *poly)
 // (one thread per block walks its bits serially with uncoalesced byte loads: only good for short blocks)
 static bool crc_use_block_kernel(int B, int A) { (void)B; return A >= 1024; }
 
+static void crc_pow_table(int A, int L, uint32_t poly, int T, CrcPow *pw)
+{
+    const uint32_t mask = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+    auto powx = [&](uint32_t e) {
+        uint32_t base = 2u, acc = 1u;
+        while (e) {
+            if (e & 1u) acc = gf2_mulmod(acc, base, L, poly, mask);
+            base = gf2_mulmod(base, base, L, poly, mask);
+            e >>= 1;
+        }
+        return acc;
+    };
+    const int chunk = (A + T - 1) / T;
+    const uint32_t xchunk = powx((uint32_t)chunk);
+    int e_next = -1;
+    for (int t = T - 1; t >= 0; --t) {
+        const int k0 = std::min(t * chunk, A), k1 = std::min(k0 + chunk, A), e = A - k1;
+        pw->p[t] = (e_next >= 0 && e == e_next + chunk) ? gf2_mulmod(pw->p[t + 1], xchunk, L, poly, mask) : powx((uint32_t)e);
+        e_next = e;
+    }
+}
+
+template <int T>
+static void crc_block_launch(const int8_t *d_in, int B, int A, int L, uint32_t poly, int mode, int8_t *d_out, uint8_t *d_err,
+                             cudaStream_t s)
+{
+    CrcPow pw;
+    crc_pow_table(A, L, poly, T, &pw);
+    crc_block_kernel<T><<<B, T, 0, s>>>(pw, d_in, A, L, poly, mode, d_out, d_err);
+}
+
 extern "C" int nrldpc_crc_encode(const int8_t *d_in, int B, int A, int poly_id, int8_t *d_out, void *stream)
 {
     int L; uint32_t poly;
@@ -307,8 +336,8 @@ extern "C" int nrldpc_crc_encode(const int8_t *d_in, int B, int A, int poly_id, 
     if (B < 0 || A < 0 || !d_in || !d_out) { set_error("crc_encode: bad argument"); return NRLDPC_EINVAL; }
     if (B == 0) return NRLDPC_OK;
     if (crc_use_block_kernel(B, A)) {
-        if (A >= 32768) crc_block_kernel<kCrcBlockThreads><<<B, kCrcBlockThreads, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 0, d_out, nullptr);
-        else crc_block_kernel<64><<<B, 64, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 0, d_out, nullptr);
+        if (A >= 32768) crc_block_launch<kCrcBlockThreads>(d_in, B, A, L, poly, 0, d_out, nullptr, (cudaStream_t)stream);
+        else crc_block_launch<64>(d_in, B, A, L, poly, 0, d_out, nullptr, (cudaStream_t)stream);
     }
     else crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 0, d_out, nullptr);
     NRLDPC_CUDA(cudaGetLastError());
@@ -322,8 +351,8 @@ extern "C" int nrldpc_crc_check(const int8_t *d_in, int B, int A, int poly_id, u
     if (B < 0 || A < 0 || !d_in || !d_err) { set_error("crc_check: bad argument"); return NRLDPC_EINVAL; }
     if (B == 0) return NRLDPC_OK;
     if (crc_use_block_kernel(B, A)) {
-        if (A >= 32768) crc_block_kernel<kCrcBlockThreads><<<B, kCrcBlockThreads, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 1, nullptr, d_err);
-        else crc_block_kernel<64><<<B, 64, 0, (cudaStream_t)stream>>>(d_in, A, L, poly, 1, nullptr, d_err);
+        if (A >= 32768) crc_block_launch<kCrcBlockThreads>(d_in, B, A, L, poly, 1, nullptr, d_err, (cudaStream_t)stream);
+        else crc_block_launch<64>(d_in, B, A, L, poly, 1, nullptr, d_err, (cudaStream_t)stream);
     }
     else crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 1, nullptr, d_err);
     NRLDPC_CUDA(cudaGetLastError());
