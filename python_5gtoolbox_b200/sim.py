@@ -146,7 +146,7 @@ class CudaBackend:
                 _lib.check(L_.nrldpc_random_bits_rows(bits.data_ptr(), mm, A, seed, first + i0 * stride, stride, s), "random_bits")
                 blk = torch.empty((mm, K), dtype=torch.int8, device=self.device)
                 _lib.check(L_.nrldpc_crc_encode(bits.data_ptr(), mm, A, poly, blk.data_ptr(), s), "crc")
-                dn = engine.encode_batch(blk.clone(), bgn, Zc)
+                dn = engine.encode_batch(blk, bgn, Zc, fix_fillers=False)   # no fillers in blk: nothing to fix, no copy needed
                 llr = torch.empty(dn.shape, dtype=torch.float32, device=self.device)
                 _lib.check(L_.nrldpc_awgn_llr_rows(dn.data_ptr(), mm, dn.shape[1], float(snr_db), seed, first + i0 * stride,
                                                    stride, llr.data_ptr(), s), "awgn")
@@ -231,7 +231,7 @@ def _device_point_counters(device, Zc, bgn, snr_db, crcpoly, L, alpha, beta, lo,
             _lib.check(L_.nrldpc_random_bits_rows(bits.data_ptr(), mm, A, seed, i0, 1, s), "random_bits")
             blk = torch.empty((mm, K), dtype=torch.int8, device=device)
             _lib.check(L_.nrldpc_crc_encode(bits.data_ptr(), mm, A, poly, blk.data_ptr(), s), "crc")
-            dn = engine.encode_batch(blk.clone(), bgn, Zc)
+            dn = engine.encode_batch(blk, bgn, Zc, fix_fillers=False)   # no fillers in blk: nothing to fix, no copy needed
             llr = torch.empty(dn.shape, dtype=torch.float32, device=device)
             _lib.check(L_.nrldpc_awgn_llr_rows(dn.data_ptr(), mm, dn.shape[1], float(snr_db), seed, i0, 1, llr.data_ptr(), s), "awgn")
             r = engine.decode_batch(llr, Zc, bgn, L, alpha, beta, early_term)
