@@ -1,0 +1,59 @@
+"""Small invocation of every kernel family, meant to run under compute-sanitizer (memcheck / racecheck /
+synccheck) on the GPU box:  compute-sanitizer --tool racecheck python tools/sanitizer_cases.py
+
+Batches are tiny (the tools slow kernels down 10-100x); no result is checked here beyond the decoder
+converging on noiseless-ish input -- parity is the job of tests/.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+from python_5gtoolbox_b200 import engine  # noqa: E402
+
+dev = "cuda:0"
+L = 6
+
+
+def one(bgn, Zc, B, snr_db=2.0):
+    K, N, Nf, M = engine.dims(bgn, Zc)
+    ck = engine.random_bits(B, K, seed=Zc, device=dev)
+    dn = engine.encode_batch(ck, bgn)
+    llr = engine.awgn_llr(dn, snr_db, seed=Zc + 1)
+    out = []
+    for et in (True, False):
+        r = engine.decode_batch(llr, Zc, bgn, L, 0.8, 0.0, et)
+        out.append(int(r["status"].sum().item()))
+    r = engine.decode_batch(llr, Zc, bgn, L, 0.8, 0.3, True, want_ck=False, want_info=True)
+    bf = engine.decode_bf_batch(llr, Zc, bgn, 4)
+    ref = engine.decode_ref_batch(llr[:1].cpu().numpy(), Zc, bgn, 2, "min-sum", 0.8, 0.0, True, f64=True)
+    torch.cuda.synchronize()
+    del bf, ref
+    print(f"BG{bgn} Zc={Zc} B={B}: converged {out[0]}/{B} (early term), {out[1]}/{B} (fixed)", flush=True)
+
+
+# spec kernel + word encoder/BF (384), spec kernel + table encoder/bf_qc (208), table-driven decoder (12, 2: many
+# codeblocks per CTA), BG2 instances
+for bgn, Zc, B in ((1, 384, 3), (2, 384, 2), (1, 208, 2), (2, 160, 2), (1, 96, 5), (1, 12, 37), (2, 2, 70)):
+    one(bgn, Zc, B)
+
+# mixed-Zc groups on side streams
+groups = []
+for bgn, Zc, B in ((1, 384, 2), (2, 352, 3), (1, 28, 9)):
+    K, N, Nf, M = engine.dims(bgn, Zc)
+    ck = engine.random_bits(B, K, seed=7 * Zc, device=dev)
+    dn = engine.encode_batch(ck, bgn)
+    groups.append((engine.awgn_llr(dn, 2.0, seed=Zc + 3), Zc, bgn))
+engine.decode_groups(groups, L, 0.8, 0.0, True)
+torch.cuda.synchronize()
+print("mixed groups ok", flush=True)
+
+# CRC attach / check on device
+for poly, n in (("24A", 8424), ("24B", 3000), ("16", 500)):
+    blk = engine.random_bits(5, n, seed=n, device=dev)
+    enc = engine.crc_encode_device(blk, poly)
+    chk = engine.crc_check_device(enc, poly)
+    torch.cuda.synchronize()
+print("crc ok", flush=True)
