@@ -1,5 +1,6 @@
 """Small invocation of every kernel family, meant to run under compute-sanitizer (memcheck / racecheck /
-synccheck) on the GPU box:  compute-sanitizer --tool racecheck python tools/sanitizer_cases.py
+synccheck) on a GPU box:  compute-sanitizer --tool racecheck python tools/sanitizer_cases.py
+(compute-sanitizer is closed on this round's pool -- rc 86 -- so only the plain run is recorded: it exits 0.)
 
 Batches are tiny (the tools slow kernels down 10-100x); no result is checked here beyond the decoder
 converging on noiseless-ish input -- parity is the job of tests/.
