@@ -19,6 +19,7 @@
 #ifndef NRLDPC_B200_H
 #define NRLDPC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -206,6 +207,67 @@ int nrldpc_raterecover_host(const void *llr_g, int in_f64, int B, int N, int Ncb
  */
 int nrldpc_harq_combine(const double *d_new, const double *d_cur, long long count, double *d_out, void *stream);
 int nrldpc_harq_combine_host(const double *nw, const double *cur, long long count, double *out);
+
+/* ------------------------------------------------------------------ whole transport blocks (callers' side, fused) */
+/*
+ * Pinned (page-locked, device-mapped) host memory from the library's pool: buffers the `_host` entry points can DMA
+ * from / into directly, and that the decoder can store its float64 soft buffer into over PCIe while it iterates.
+ * Pageable buffers are accepted everywhere; they are staged through a ring of pinned slots by copy threads.
+ */
+int nrldpc_host_alloc(size_t bytes, void **p);
+int nrldpc_host_free(void *p);
+
+/*
+ * De-rate-matching + HARQ combining of the C codeblocks of a transport block without a decoder behind it:
+ * nr_ldpc_raterecover.raterecover_ldpc (py5gphy/ldpc/nr_ldpc_raterecover.py:6-65) followed by the combining loop of
+ * DLSCHDecode / ULSCH_decoding (py5gphy/nr_pdsch/nr_dlsch_decode.py:74-87, py5gphy/nr_pusch/nr_ulsch_decode.py:75-88).
+ *   llr_g  concatenated received LLRs (float32, or float64 when in_f64), E [C], goff [C] offsets inside llr_g,
+ *   cur    [C,N] float64 soft buffer of the earlier transmissions, or NULL (first transmission / HARQ off),
+ *   soft   [C,N] float64 out (new_LLr_dns), llr32 [C,N] float32 out (the decoder's input); either may be NULL.
+ */
+int nrldpc_sch_recover(const void *d_llr_g, int in_f64, int C, int N, int Ncb, int k0, int Qm, int F0, int F1,
+                       const int32_t *d_E, const long long *d_goff, const double *d_cur, double *d_soft, float *d_llr32,
+                       void *stream);
+int nrldpc_sch_recover_host(const void *llr_g, int in_f64, int C, int N, int Ncb, int k0, int Qm, int Zc, int K_apo, int K,
+                            const int32_t *E, const double *cur, double *soft);
+
+/*
+ * DLSCHDecode / ULSCH_decoding with algo = 'min-sum' after the parameter arithmetic
+ * (py5gphy/nr_pdsch/nr_dlsch_decode.py:56-107, py5gphy/nr_pusch/nr_ulsch_decode.py:56-108) in two launches:
+ *   1. the min-sum decoder, whose LLR load is the rate recovery and HARQ combining above (per codeblock: received
+ *      sequence -> fp32 row that stays in L2 + the float64 row of `soft`), reference early termination;
+ *   2. CB CRC24B of every codeblock when C > 1 (:93-98, computed and ignored by the reference), the cbz payload bits
+ *      of every codeblock into the transport block (:101-102) and the TB CRC (:105).
+ *   K_apo = cbz + L of ldpc_info.get_cbs_info (fillers are [K_apo, K)); A = TBSize; C * cbz = A + (24 | 16).
+ *   tbblk [A] int8, tb_err[0] = 1 when the TB CRC fails (status = not tb_err), cb_err [C], status [C] = LDPC parity
+ *   ok, iters [C]; ck [C,N'] = the codeblocks' hard decisions (device variant: NULL = internal workspace).
+ * Host variant: synchronous; when `soft` is pinned host memory (nrldpc_host_alloc) the decoder stores into it directly.
+ */
+int nrldpc_sch_decode(const void *d_llr_g, int in_f64, int C, int bgn, int Zc, int Ncb, int k0, int Qm, int K_apo,
+                      const int32_t *d_E, const long long *d_goff, const double *d_cur, double *d_soft, int max_iter,
+                      float alpha, float beta, int A, int8_t *d_ck, int8_t *d_tbblk, uint8_t *d_tb_err, uint8_t *d_cb_err,
+                      uint8_t *d_status, int32_t *d_iters, void *stream);
+int nrldpc_sch_decode_host(const void *llr_g, int in_f64, int C, int bgn, int Zc, int Ncb, int k0, int Qm, int K_apo,
+                           const int32_t *E, const double *cur, double *soft, int max_iter, float alpha, float beta, int A,
+                           int8_t *tbblk, uint8_t *tb_err, uint8_t *cb_err, uint8_t *status, int32_t *iters);
+
+/*
+ * Transmit side.  nrldpc_sch_segment: TB CRC attachment (crc.nr_crc_encode with '24A' | '16',
+ * py5gphy/nr_pdsch/nr_dlsch.py:29-35) + nr_ldpc_cbsegment.ldpc_cbsegment (py5gphy/ldpc/nr_ldpc_cbsegment.py:7-33):
+ * trblk int8 [A] -> cbs int8 [C,K] with CB CRC24B when C > 1 and -1 fillers.
+ * nrldpc_encode_ratematch: the per-codeblock loop of DLSCHEncode / ULSCH_encoding_ratematch (nr_dlsch.py:53-72,
+ * py5gphy/nr_pusch/nr_ulsch.py:49-66): encode_ldpc, ratematch_ldpc and code block concatenation, cbs [C,K] -> g [sum E]
+ * (fix_fillers: the -1 fillers of cbs become 0 in place like encode_ldpc does).
+ * nrldpc_sch_encode_host: both, trblk -> g, nothing but the two ends crossing PCIe.
+ */
+int nrldpc_sch_segment(const int8_t *d_trblk, int A, int C, int K, int8_t *d_cbs, void *stream);
+int nrldpc_sch_segment_host(const int8_t *trblk, int A, int C, int K, int8_t *cbs);
+int nrldpc_encode_ratematch(int8_t *d_cbs, int C, int bgn, int Zc, int fix_fillers, int Ncb, int k0, int Qm,
+                            const int32_t *d_E, const long long *d_goff, int8_t *d_g, void *stream);
+int nrldpc_encode_ratematch_host(int8_t *cbs, int C, int bgn, int Zc, int fix_fillers, int Ncb, int k0, int Qm,
+                                 const int32_t *E, int8_t *g);
+int nrldpc_sch_encode_host(const int8_t *trblk, int A, int C, int bgn, int Zc, int Ncb, int k0, int Qm, const int32_t *E,
+                           int8_t *g);
 
 #ifdef __cplusplus
 }

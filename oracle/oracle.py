@@ -157,6 +157,15 @@ def nr_crc_encode(blk, poly):
     return out[: blk.size + L].copy()
 
 
+def crc_decode(blkandcrc, poly):
+    """(blk, err) of py5gphy/crc/crc.py:43-88 (mask=0): the long division of the whole block leaves a zero remainder
+    exactly when the CRC of the first A bits equals the last L bits."""
+    x = np.ascontiguousarray(blkandcrc, np.int8)
+    L = {"6": 6, "11": 11, "16": 16, "24A": 24, "24B": 24, "24C": 24}[poly.upper()]
+    A = x.size - L
+    return x[:A].copy(), int(not np.array_equal(nr_crc_encode(x[:A], poly), x))
+
+
 def ratematch_ldpc(dn, Ncb, E, k0, Qm):
     """py5gphy/ldpc/nr_ldpc_ratematch.py:64-97"""
     dn = np.ascontiguousarray(dn, np.int8)

@@ -66,6 +66,17 @@ def _declare(L):
         "nrldpc_raterecover_host": (i, [p, i, i, i, i, i, i, i, i, i, p, p, i]),
         "nrldpc_harq_combine": (i, [p, p, ll, p, p]),
         "nrldpc_harq_combine_host": (i, [p, p, ll, p]),
+        "nrldpc_host_alloc": (i, [c.c_size_t, c.POINTER(p)]),
+        "nrldpc_host_free": (i, [p]),
+        "nrldpc_sch_recover": (i, [p, i, i, i, i, i, i, i, i, p, p, p, p, p, p]),
+        "nrldpc_sch_recover_host": (i, [p, i, i, i, i, i, i, i, i, i, p, p, p]),
+        "nrldpc_sch_decode": (i, [p, i, i, i, i, i, i, i, i, p, p, p, p, i, f, f, i, p, p, p, p, p, p, p]),
+        "nrldpc_sch_decode_host": (i, [p, i, i, i, i, i, i, i, i, p, p, p, i, f, f, i, p, p, p, p, p]),
+        "nrldpc_sch_segment": (i, [p, i, i, i, p, p]),
+        "nrldpc_sch_segment_host": (i, [p, i, i, i, p]),
+        "nrldpc_encode_ratematch": (i, [p, i, i, i, i, i, i, i, p, p, p, p]),
+        "nrldpc_encode_ratematch_host": (i, [p, i, i, i, i, i, i, i, p, p]),
+        "nrldpc_sch_encode_host": (i, [p, i, i, i, i, i, i, i, p, p]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError here = the .so does not export what the header declares

@@ -30,7 +30,7 @@ int cuda_fail(cudaError_t e, const char *what)
 }
 
 // (bgn, Zc) -> quasi-cyclic tables, built once
-static const QcCfg *get_cfg(int bgn, int Zc)
+const QcCfg *get_cfg(int bgn, int Zc)
 {
     static std::mutex mu;
     static std::map<int, QcCfg *> cache;
@@ -46,6 +46,33 @@ static const QcCfg *get_cfg(int bgn, int Zc)
     }
     cache[key] = c;
     return c;
+}
+
+cudaError_t lib_mempool(cudaMemPool_t *pool)
+{
+    constexpr int kMaxDev = 64;
+    static std::mutex mu;
+    static cudaMemPool_t pools[kMaxDev] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDev) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t p;
+        e = cudaMemPoolCreate(&p, &props);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = 1ull << 30;  // freed scratch beyond 1 GiB goes back to the driver at the next synchronisation
+        cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[dev] = p;
+    }
+    *pool = pools[dev];
+    return cudaSuccess;
 }
 
 using DevBuf = ScratchBuf;
@@ -317,16 +344,26 @@ int nrldpc_decode_minsum_geometry(int bgn, int Zc, int *cbs_per_cta, int *thread
     return decode_minsum_geometry(*c, cbs_per_cta, threads, smem_bytes);
 }
 
-// Host-buffer entry point: a ring of kHostStages chunks so that (with pinned host memory) the H2D copy of
-// chunk i+1 and the D2H copy of chunk i-1 overlap the decode of chunk i.  The stages' device buffers and
-// streams are created once per device and reused (grow-only) by later calls.  The path is bound by the
-// host link (101 KB of LLRs per codeblock), so the chunks are kept small: the only exposed time is the
-// first chunk's copy and the last chunk's decode.
+// Host-buffer entry point: a ring of kHostStages chunks so that the H2D copy of chunk i+1 and the D2H copy of chunk
+// i-1 overlap the decode of chunk i.  The stages' device buffers, pinned result mirrors and streams are created once
+// per device and reused (grow-only) by later calls; every device has its own ring and lock.  The path is bound by the
+// host link (101 KB of LLRs per codeblock), so the chunks are kept small: the only exposed time is the first chunk's
+// copy and the last chunk's decode.  Pinned caller memory goes straight to the DMA engine; pageable caller memory
+// (what a NumPy caller hands over) is staged through pinned slots by copy threads (h2d_async), and results destined
+// for pageable memory land in the stage's pinned mirror first and are copied out when the stage is next touched --
+// a cudaMemcpyAsync to / from pageable memory would block the host until the stage's kernel is done and serialise
+// the ring.
 namespace {
 struct HostStage {
-    void *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // llr, ck, info, status, iters
+    void *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // device: llr, ck, info, status, iters
     size_t cap[5] = {0, 0, 0, 0, 0};
+    void *mir[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // pinned host mirrors of the four result buffers
+    size_t mcap[5] = {0, 0, 0, 0, 0};
     cudaStream_t s = nullptr;
+    // results of the chunk in flight that still have to be copied out of the mirrors
+    bool busy = false;
+    struct Out { void *dst; int which; size_t bytes; } out[4];
+    int nout = 0;
     int ensure(int which, size_t bytes)
     {
         if (bytes <= cap[which]) return NRLDPC_OK;
@@ -335,14 +372,48 @@ struct HostStage {
         cap[which] = bytes;
         return NRLDPC_OK;
     }
+    int ensure_mirror(int which, size_t bytes)
+    {
+        if (bytes <= mcap[which]) return NRLDPC_OK;
+        if (mir[which]) { NRLDPC_CUDA(cudaFreeHost(mir[which])); mir[which] = nullptr; mcap[which] = 0; }
+        NRLDPC_CUDA(cudaHostAlloc(&mir[which], bytes, cudaHostAllocPortable));
+        mcap[which] = bytes;
+        return NRLDPC_OK;
+    }
+    // wait for the chunk in flight and hand its mirrored results to the caller
+    int drain()
+    {
+        if (!busy) return NRLDPC_OK;
+        busy = false;
+        NRLDPC_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < nout; ++i) host_copy(out[i].dst, mir[out[i].which], out[i].bytes);
+        nout = 0;
+        return NRLDPC_OK;
+    }
 };
 constexpr int kHostStages = 3;
 constexpr size_t kHostChunkBytes = (size_t)32 << 20;
 struct HostPipe {
     std::mutex mu;
-    std::map<int, std::array<HostStage, kHostStages>> per_device;
+    std::array<HostStage, kHostStages> st;
 };
-HostPipe g_pipe;
+HostPipe *host_pipe()
+{
+    static std::mutex mu;
+    static std::map<int, HostPipe *> per_device;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = per_device.find(dev);
+    if (it == per_device.end()) it = per_device.emplace(dev, new HostPipe).first;
+    return it->second;
+}
+bool host_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
 }  // namespace
 
 int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
@@ -352,40 +423,56 @@ int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_
     if (!c) return NRLDPC_EINVAL;
     if (B < 0 || max_iter < 0 || !llr) { set_error("decode_minsum: bad argument"); return NRLDPC_EINVAL; }
     if (B == 0) return NRLDPC_OK;
-    int dev = 0;
-    NRLDPC_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_pipe.mu);
-    auto &ring = g_pipe.per_device[dev];
-    HostStage *st[kHostStages];
-    for (int i = 0; i < kHostStages; ++i) st[i] = &ring[i];
+    HostPipe *pipe = host_pipe();
+    if (!pipe) return cuda_fail(cudaGetLastError(), "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(pipe->mu);
+    HostStage *st = pipe->st.data();
     const size_t llr_bytes = (size_t)c->N * 4, nwords = (size_t)(c->K + 31) / 32;
     int chunk = (int)std::max<size_t>(1, kHostChunkBytes / llr_bytes);
     if (chunk > B) chunk = (B + 1) / 2 > 256 ? (B + 1) / 2 : B;  // two chunks still overlap copy and compute
     const int nstage = std::min(kHostStages, (B + chunk - 1) / chunk);
-    for (int i = 0; i < nstage; ++i) {
-        if (!st[i]->s) NRLDPC_CUDA(cudaStreamCreateWithFlags(&st[i]->s, cudaStreamNonBlocking));
-        if (int rc = st[i]->ensure(0, (size_t)chunk * llr_bytes)) return rc;
-        if (ck) if (int rc = st[i]->ensure(1, (size_t)chunk * c->Nfull)) return rc;
-        if (info_packed) if (int rc = st[i]->ensure(2, (size_t)chunk * nwords * 4)) return rc;
-        if (int rc = st[i]->ensure(3, (size_t)chunk)) return rc;
-        if (int rc = st[i]->ensure(4, (size_t)chunk * 4)) return rc;
+    // where the four results go: {caller pointer, bytes per codeblock, pinned?}
+    struct Res { char *p; size_t per; bool pinned; } res[5] = {
+        {nullptr, 0, true}, {(char *)ck, (size_t)c->Nfull, false}, {(char *)info_packed, nwords * 4, false},
+        {(char *)status, 1, false}, {(char *)iters, 4, false}};
+    for (int w = 1; w < 5; ++w) if (res[w].p) res[w].pinned = host_pinned(res[w].p);
+    int rc = NRLDPC_OK;
+    auto fail = [&](int code) {  // no copy may still be in flight into the caller's buffers when we return
+        for (int i = 0; i < nstage; ++i) { if (st[i].s) cudaStreamSynchronize(st[i].s); st[i].busy = false; st[i].nout = 0; }
+        return code;
+    };
+    for (int i = 0; i < nstage && rc == NRLDPC_OK; ++i) {
+        if (!st[i].s && cudaStreamCreateWithFlags(&st[i].s, cudaStreamNonBlocking) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamCreate");
+        if (rc == NRLDPC_OK) rc = st[i].ensure(0, (size_t)chunk * llr_bytes);
+        for (int w = 1; w < 5 && rc == NRLDPC_OK; ++w) {
+            if (w <= 2 && !res[w].p) continue;  // ck / info are optional kernel outputs; status and iters are always produced
+            rc = st[i].ensure(w, (size_t)chunk * res[w].per);
+            if (rc == NRLDPC_OK && res[w].p && !res[w].pinned) rc = st[i].ensure_mirror(w, (size_t)chunk * res[w].per);
+        }
     }
+    if (rc != NRLDPC_OK) return fail(rc);
     int k = 0;
     for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
-        HostStage &S = *st[k % nstage];
+        HostStage &S = st[k % nstage];
         const int nb = std::min(chunk, B - b0);
-        NRLDPC_CUDA(cudaMemcpyAsync(S.buf[0], llr + (size_t)b0 * c->N, (size_t)nb * llr_bytes, cudaMemcpyHostToDevice, S.s));
-        if (int rc = launch_decode_minsum(*c, (const float *)S.buf[0], nb, max_iter, alpha, beta, early_term,
-                                          ck ? (int8_t *)S.buf[1] : nullptr, info_packed ? (uint32_t *)S.buf[2] : nullptr,
-                                          (uint8_t *)S.buf[3], (int32_t *)S.buf[4], S.s))
-            return rc;
-        if (ck) NRLDPC_CUDA(cudaMemcpyAsync(ck + (size_t)b0 * c->Nfull, S.buf[1], (size_t)nb * c->Nfull, cudaMemcpyDeviceToHost, S.s));
-        if (info_packed)
-            NRLDPC_CUDA(cudaMemcpyAsync(info_packed + (size_t)b0 * nwords, S.buf[2], (size_t)nb * nwords * 4, cudaMemcpyDeviceToHost, S.s));
-        if (status) NRLDPC_CUDA(cudaMemcpyAsync(status + b0, S.buf[3], (size_t)nb, cudaMemcpyDeviceToHost, S.s));
-        if (iters) NRLDPC_CUDA(cudaMemcpyAsync(iters + b0, S.buf[4], (size_t)nb * 4, cudaMemcpyDeviceToHost, S.s));
+        if ((rc = S.drain()) != NRLDPC_OK) return fail(rc);
+        if ((rc = h2d_async(S.buf[0], llr + (size_t)b0 * c->N, (size_t)nb * llr_bytes, S.s)) != NRLDPC_OK) return fail(rc);
+        if ((rc = launch_decode_minsum(*c, (const float *)S.buf[0], nb, max_iter, alpha, beta, early_term,
+                                       ck ? (int8_t *)S.buf[1] : nullptr, info_packed ? (uint32_t *)S.buf[2] : nullptr,
+                                       (uint8_t *)S.buf[3], (int32_t *)S.buf[4], S.s)) != NRLDPC_OK)
+            return fail(rc);
+        for (int w = 1; w < 5; ++w) {
+            if (!res[w].p) continue;
+            const size_t bytes = (size_t)nb * res[w].per;
+            char *dst = res[w].p + (size_t)b0 * res[w].per;
+            cudaError_t e = cudaMemcpyAsync(res[w].pinned ? (void *)dst : S.mir[w], S.buf[w], bytes, cudaMemcpyDeviceToHost, S.s);
+            if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpyAsync(D2H)"));
+            if (!res[w].pinned) S.out[S.nout++] = {dst, w, bytes};
+        }
+        S.busy = true;
     }
-    for (int i = 0; i < nstage; ++i) NRLDPC_CUDA(cudaStreamSynchronize(st[i]->s));
+    for (int i = 0; i < nstage; ++i)
+        if ((rc = st[i].drain()) != NRLDPC_OK) return fail(rc);
     return NRLDPC_OK;
 }
 

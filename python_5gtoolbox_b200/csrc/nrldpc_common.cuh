@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include "../../include/nrldpc_b200.h"
 
 namespace nrldpc {
@@ -48,6 +49,16 @@ int build_qc_cfg(int bgn, int Zc, QcCfg *cfg);
 int find_ils(int Zc);
 int build_csr(int bgn, int Zc, int32_t *rowptr, int32_t *colidx);
 
+// (bgn, Zc) -> quasi-cyclic tables, built once; nullptr (and the error text set) for an invalid pair (nrldpc_api.cu)
+const QcCfg *get_cfg(int bgn, int Zc);
+
+// host <-> device staging shared by the host-buffer entry points (nrldpc_sch.cu): pinned memory goes straight to the
+// DMA engine, pageable memory through a ring of pinned slots filled by copy threads
+void host_copy(void *dst, const void *src, size_t n);
+int h2d_async(void *dst, const void *src, size_t n, cudaStream_t s);
+int d2h_sync(void *dst, const void *src, size_t n, cudaStream_t s);
+int host_stream(cudaStream_t *s);
+
 // error plumbing (nrldpc_api.cu)
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
@@ -58,36 +69,35 @@ int cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
-// Temporary device buffer of the synchronous host-buffer entry points: stream-ordered allocation from the
-// device's default memory pool (kept warm: release threshold = never), so a per-codeblock call of an unchanged
-// reference script does not pay a cudaMalloc / cudaFree pair per buffer.
+// The library's own stream-ordered memory pool on the current device (nrldpc_api.cu): keeps up to 1 GiB of freed
+// scratch memory for reuse and gives the rest back at the next synchronisation.  The device's default pool, which
+// the embedding application (PyTorch, ...) may use, is never touched.
+cudaError_t lib_mempool(cudaMemPool_t *pool);
+
+// Temporary device buffer: stream-ordered allocation from lib_mempool(), so a per-codeblock call of an unchanged
+// reference script does not pay a cudaMalloc / cudaFree pair per buffer.  Freed on the stream it was allocated on.
 struct ScratchBuf {
     void *p = nullptr;
-    cudaError_t alloc(size_t n)
+    cudaStream_t s = nullptr;
+    cudaError_t alloc(size_t n, cudaStream_t stream = nullptr)
     {
-        static thread_local int warmed_dev = -1;
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
+        cudaMemPool_t pool;
+        cudaError_t e = lib_mempool(&pool);
         if (e != cudaSuccess) return e;
-        if (warmed_dev != dev) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            warmed_dev = dev;
-        }
-        return cudaMallocAsync(&p, n ? n : 1, (cudaStream_t)0);
+        s = stream;
+        return cudaMallocFromPoolAsync(&p, n ? n : 1, pool, s);
     }
-    ~ScratchBuf() { if (p) cudaFreeAsync(p, (cudaStream_t)0); }
+    ~ScratchBuf() { if (p) cudaFreeAsync(p, s); }
     template <typename T> T *as() { return static_cast<T *>(p); }
 };
 
 // kernel launchers (device pointers)
 int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s);
+struct RrArgs;  // nrldpc_raterecover.cuh
+// rr != nullptr: the LLR load is the rate recovery of a transport block (d_llr unused, early_term must be 1)
 int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_iter, float alpha, float beta,
                          int early_term, int8_t *d_ck, uint32_t *d_info, uint8_t *d_status, int32_t *d_iters,
-                         cudaStream_t s);
+                         cudaStream_t s, const RrArgs *rr = nullptr);
 int decode_minsum_geometry(const QcCfg &cfg, int *G, int *threads, int *smem);
 
 template <typename T>

@@ -2,6 +2,7 @@
 // specialised (nrldpc_decode_spec.cu) flooding min-sum decoder kernels.
 #pragma once
 #include "nrldpc_common.cuh"
+#include "nrldpc_raterecover.cuh"
 
 namespace nrldpc {
 
@@ -13,12 +14,18 @@ struct DecArgs {
     uint32_t *info;
     uint8_t *status;
     int32_t *iters;
-    int *work = nullptr;  // early-termination kernels: {ticket counter, CTAs done} slot of the dynamic codeblock queue, both zero
-                          // at launch and zeroed again by the last CTA (or null: static stride)
+    // early-termination kernels: ticket counter of the dynamic codeblock queue (or null: static stride).  The counter is
+    // never reset: a launch draws exactly B tickets (one per decoded codeblock), so the host knows the value it has when
+    // the launch starts (work_base) and the kernel's ticket is atomicAdd(work, 1) - work_base.
+    unsigned *work = nullptr;
+    unsigned work_base = 0;
+    RrArgs rr;  // rr.src != nullptr: the LLR load is the rate recovery of a transport block (llr is then unused)
 };
 
-// next slot of the current device's ring of queue slots (nrldpc_decode_spec.cu)
-int decode_queue_slot(int **slot);
+// Ticket counter for a launch that will draw `tickets` tickets on stream s, from the current device's ring of counters
+// (nrldpc_decode_spec.cu).  *work = nullptr when the stream is being captured into a CUDA graph (a replay would reuse
+// work_base): the caller then falls back to the static stride.
+int decode_queue_slot(cudaStream_t s, unsigned tickets, unsigned **work, unsigned *work_base);
 
 constexpr uint32_t kInfBits = 0x7f800000u;
 

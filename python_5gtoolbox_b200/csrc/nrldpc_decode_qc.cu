@@ -88,14 +88,16 @@ struct Me {               // what a thread owns for the whole kernel
     bool valid;
 };
 
-__device__ __forceinline__ float load_llr(const Me &me, uint32_t off)
+// RR: the rows were written by this CTA (fused rate recovery): L2-coherent load instead of the read-only path
+template <bool RR> __device__ __forceinline__ float load_llr(const Me &me, uint32_t off)
 {
-    return __fadd_rn(__ldg(reinterpret_cast<const float *>(me.llr + (me.llr_off + off))), 0.0f);  // -0.0 -> +0.0
+    const float *p = reinterpret_cast<const float *>(me.llr + (me.llr_off + off));
+    return __fadd_rn(RR ? __ldcg(p) : __ldg(p), 0.0f);  // -0.0 -> +0.0
 }
 
 // One check row (row-block i, lifted index r): syndrome bit of the current hard decisions, then the
 // min-sum update of its record from Lq = LQ - Lr_old.  py5gphy/ldpc/nr_ldpc_decode.py:107-123,178-227.
-template <int DEG, bool EXT, bool WIDE, bool ET>
+template <int DEG, bool EXT, bool WIDE, bool ET, bool RR>
 __device__ __forceinline__ void cn_row(const DecTab &T, const DecArgs &a, const Me &me, const int i, const bool active,
                                        int *flag)
 {
@@ -109,7 +111,7 @@ __device__ __forceinline__ void cn_row(const DecTab &T, const DecArgs &a, const 
     const float2 m = *reinterpret_cast<const float2 *>(rec);
     const uint32_t bits = WIDE ? *reinterpret_cast<const uint32_t *>(bp) : *reinterpret_cast<const uint16_t *>(bp);
     float llr_e = 0.f;
-    if (EXT) llr_e = load_llr(me, ri.ext_llr);
+    if (EXT) llr_e = load_llr<RR>(me, ri.ext_llr);
     const uint2 *et = me.tcn + ri.e0;
 
     float vmin = __uint_as_float(kInfBits);  // sign = running sign product, |vmin| = first minimum
@@ -154,36 +156,37 @@ __device__ __forceinline__ void cn_row(const DecTab &T, const DecArgs &a, const 
 }
 
 // All rows of one class that belong to this warp's group.
-template <int CLS, int DEG, bool EXT, bool WIDE, bool ET>
+template <int CLS, int DEG, bool EXT, bool WIDE, bool ET, bool RR>
 __device__ __forceinline__ void cn_class(const DecTab &T, const DecArgs &a, const Me &me, int sub, bool active, int *flag)
 {
     const int e = T.cls_end[CLS * kMaxS + sub];
-    for (int o = T.cls_begin[CLS * kMaxS + sub]; o < e; ++o) cn_row<DEG, EXT, WIDE, ET>(T, a, me, T.cn_list[o], active, flag);
+    for (int o = T.cls_begin[CLS * kMaxS + sub]; o < e; ++o) cn_row<DEG, EXT, WIDE, ET, RR>(T, a, me, T.cn_list[o], active, flag);
 }
 
-template <bool ET>
+template <bool ET, bool RR>
 __device__ __forceinline__ void cn_pass(const DecTab &T, const DecArgs &a, const Me &me, int sub, bool active, int *flag)
 {
-    cn_class<0, 19, false, true, ET>(T, a, me, sub, active, flag);
-    cn_class<1, 10, false, false, ET>(T, a, me, sub, active, flag);
-    cn_class<2, 8, false, false, ET>(T, a, me, sub, active, flag);
-    cn_class<3, 10, true, false, ET>(T, a, me, sub, active, flag);
-    cn_class<4, 9, true, false, ET>(T, a, me, sub, active, flag);
-    cn_class<5, 8, true, false, ET>(T, a, me, sub, active, flag);
-    cn_class<6, 7, true, false, ET>(T, a, me, sub, active, flag);
-    cn_class<7, 6, true, false, ET>(T, a, me, sub, active, flag);
-    cn_class<8, 5, true, false, ET>(T, a, me, sub, active, flag);
-    cn_class<9, 4, true, false, ET>(T, a, me, sub, active, flag);
-    cn_class<10, 3, true, false, ET>(T, a, me, sub, active, flag);
+    cn_class<0, 19, false, true, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<1, 10, false, false, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<2, 8, false, false, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<3, 10, true, false, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<4, 9, true, false, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<5, 8, true, false, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<6, 7, true, false, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<7, 6, true, false, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<8, 5, true, false, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<9, 4, true, false, ET, RR>(T, a, me, sub, active, flag);
+    cn_class<10, 3, true, false, ET, RR>(T, a, me, sub, active, flag);
 }
 
 // One core variable (column-block j, lifted index c = me.r): LQ = LLRin + sum_i Lr(i) in ascending
 // row-block order = ascending check index (py5gphy/ldpc/nr_ldpc_decode.py:126).
+template <bool RR>
 __device__ __forceinline__ void vn_col(const DecTab &T, const Me &me, int j, bool active)
 {
     const ColInfo ci = T.col[j];
     float lv = 0.f;  // the 2Zc punctured systematic bits start at LLR 0 (:43)
-    if (ci.llr_off != kNoLlr) lv = load_llr(me, ci.llr_off);
+    if (ci.llr_off != kNoLlr) lv = load_llr<RR>(me, ci.llr_off);
     const uint32_t c8 = (uint32_t)me.r * 8u, Z8 = (uint32_t)T.Z8;
     float acc = 0.f;
     const uint4 *q = me.tvn + ci.q0;
@@ -209,6 +212,7 @@ __device__ __forceinline__ void vn_col(const DecTab &T, const Me &me, int j, boo
 // Syndrome pass without a record update, with the post-loop tie rule LQ<=0 -> 1
 // (py5gphy/ldpc/nr_ldpc_decode.py:134-143).  Also stores the hard decisions of the extension
 // variables, which have no resident posterior.
+template <bool RR>
 __device__ __forceinline__ void final_row(const DecTab &T, const Me &me, int i, bool active, int *flag)
 {
     const RowInfo ri = T.row[i];
@@ -227,7 +231,7 @@ __device__ __forceinline__ void final_row(const DecTab &T, const Me &me, int i, 
         const float2 m = *reinterpret_cast<const float2 *>(me.mags + rel);
         const uint32_t bits = *reinterpret_cast<const uint16_t *>(me.bn + (rel >> 2));
         const float lr = record_lr(m, ((bits ^ ((uint32_t)(deg - 1) << 12)) & 0xf000u) == 0, bits << 31);
-        const float x = __fadd_rn(load_llr(me, ri.ext_llr), lr);
+        const float x = __fadd_rn(load_llr<RR>(me, ri.ext_llr), lr);
         const bool hb1 = x <= 0.f;
         const uint32_t hb = __ballot_sync(0xffffffffu, hb1);
         if (active && (me.r & (T.lanes - 1)) == 0)
@@ -237,7 +241,7 @@ __device__ __forceinline__ void final_row(const DecTab &T, const Me &me, int i, 
     if (active && synd) flag[me.g] = 1;
 }
 
-template <int MAXNT, bool ET>
+template <int MAXNT, bool ET, bool RR = false>
 __global__ void __launch_bounds__(MAXNT, 1)
 decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ DecArgs a)
 {
@@ -261,12 +265,19 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
         me.mags = me.slot + T.off_mags;
         me.bw = me.slot + T.off_bw;
         me.bn = me.slot + T.off_bn;
-        me.llr = reinterpret_cast<const char *>(a.llr + (size_t)cb0 * T.N);
+        me.llr = reinterpret_cast<const char *>((RR ? a.rr.scratch : a.llr) + (size_t)cb0 * T.N);
         me.llr_off = (uint32_t)(((cb < a.B) ? g : a.B - 1 - cb0) * T.N + me.r) * 4u;
         me.tcn = reinterpret_cast<const uint2 *>(smem + T.tab_cn);
         me.tvn = reinterpret_cast<const uint4 *>(smem + T.tab_vn);
     }
 
+    if constexpr (RR) {
+        // the LLR load is the rate recovery (+ HARQ combining) of the CTA's codeblocks: received sequence -> their fp32 rows
+        // (read back below through L2) and the float64 soft buffer the caller keeps.  Shared memory is not in use yet.
+        for (int g = 0; g < G && cb0 + g < a.B; ++g)
+            rr_row(a.rr, cb0 + g, T.N, a.rr.scratch + (size_t)(cb0 + g) * T.N, reinterpret_cast<double *>(smem));
+        __syncthreads();
+    }
     // ---- init: records = 0 (Lr = 0, :101), tables staged, LQ = LLRin (:94) with the punctured columns at 0 (:43)
     {
         uint32_t *w = reinterpret_cast<uint32_t *>(smem);
@@ -286,7 +297,7 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
     if (me.valid)
         for (int o = sub; o < T.ncore; o += T.S) {
             const ColInfo ci = T.col[o];
-            if (ci.llr_off != kNoLlr) *reinterpret_cast<float *>(me.slot + ci.lq_off + me.r * 4) = load_llr(me, ci.llr_off);
+            if (ci.llr_off != kNoLlr) *reinterpret_cast<float *>(me.slot + ci.lq_off + me.r * 4) = load_llr<RR>(me, ci.llr_off);
         }
     __syncthreads();
 
@@ -297,7 +308,7 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
         int *flag = s_flag[it & 1];
         const bool active = me.valid && !((donemask >> me.g) & 1u);
         // ---- check-node pass (+ syndrome of the current hard decisions when ET)
-        if (__any_sync(0xffffffffu, active)) cn_pass<ET>(T, a, me, sub, active, flag);
+        if (__any_sync(0xffffffffu, active)) cn_pass<ET, RR>(T, a, me, sub, active, flag);
         __syncthreads();
         if (ET) {
             for (int g = 0; g < G; ++g)
@@ -313,7 +324,7 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
         const bool active2 = me.valid && !((donemask >> me.g) & 1u);
         if (__any_sync(0xffffffffu, active2)) {
             const int e = T.vn_end[sub];
-            for (int o = T.vn_begin[sub]; o < e; ++o) vn_col(T, me, T.vn_list[o], active2);
+            for (int o = T.vn_begin[sub]; o < e; ++o) vn_col<RR>(T, me, T.vn_list[o], active2);
         }
         __syncthreads();
     }
@@ -323,7 +334,7 @@ decode_minsum_kernel(const __grid_constant__ DecTab T, const __grid_constant__ D
     if (donemask != fullmask) {
         int *flag = s_flag[it & 1];  // cleared, not yet written
         const bool active = me.valid && !((donemask >> me.g) & 1u);
-        for (int o = sub; o < T.nrows; o += T.S) final_row(T, me, o, active, flag);
+        for (int o = sub; o < T.nrows; o += T.S) final_row<RR>(T, me, o, active, flag);
         __syncthreads();
         for (int g = 0; g < G; ++g)
             if (!((donemask >> g) & 1u) && flag[g] == 0) okmask |= 1u << g;
@@ -521,7 +532,7 @@ int decode_minsum_geometry(const QcCfg &cfg, int *G_out, int *threads, int *smem
 
 int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_iter, float alpha, float beta,
                          int early_term, int8_t *d_ck, uint32_t *d_info, uint8_t *d_status, int32_t *d_iters,
-                         cudaStream_t s)
+                         cudaStream_t s, const RrArgs *rr)
 {
     if (B <= 0) return NRLDPC_OK;
     const DecTab *T = get_dec_tab(cfg);
@@ -529,6 +540,10 @@ int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_it
     DecArgs a;
     a.llr = d_llr; a.B = B; a.max_iter = max_iter; a.alpha = alpha; a.beta = beta;
     a.ck = d_ck; a.info = d_info; a.status = d_status; a.iters = d_iters;
+    if (rr) {
+        if (!early_term || !rr->src || !rr->E || !rr->goff) { set_error("decode: the fused rate recovery needs early_term = 1 and src, E, goff"); return NRLDPC_EINVAL; }
+        a.rr = *rr;
+    }
     static const bool no_spec = std::getenv("NRLDPC_NO_SPEC") != nullptr;  // tests: force the generic kernel
     if (!no_spec) {
         bool handled = false;
@@ -536,12 +551,18 @@ int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_it
         if (handled) return rc;
     }
     const int grid = (B + T->G - 1) / T->G, nt = T->nwarps * 32, smem = T->smem_bytes;
+    ScratchBuf rows;  // fused rate recovery: the recovered fp32 rows [B, N], stream-ordered
+    if (rr && !a.rr.scratch) {
+        NRLDPC_CUDA(rows.alloc((size_t)B * T->N * sizeof(float), s));
+        a.rr.scratch = rows.as<float>();
+    }
     auto launch = [&](auto kern) -> int {
         NRLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         kern<<<grid, nt, smem, s>>>(*T, a);
         NRLDPC_CUDA(cudaGetLastError());
         return NRLDPC_OK;
     };
+    if (rr) return nt <= 768 ? launch(decode_minsum_kernel<768, true, true>) : launch(decode_minsum_kernel<1024, true, true>);
     if (nt <= 768) return early_term ? launch(decode_minsum_kernel<768, true>) : launch(decode_minsum_kernel<768, false>);
     return early_term ? launch(decode_minsum_kernel<1024, true>) : launch(decode_minsum_kernel<1024, false>);
 }

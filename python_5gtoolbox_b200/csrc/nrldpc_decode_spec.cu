@@ -22,24 +22,38 @@ int launch_decode_spec(int bgn, int Zc, const DecArgs &a, int early_term, cudaSt
     return NRLDPC_OK;
 }
 
-// Ring of {ticket, done} slots per device for the dynamic codeblock queue of the early-termination kernels.  A slot is
-// zero whenever no kernel is using it (the last CTA of a launch zeroes it), so a launch only draws the next index;
-// two launches share a slot only if kSlots launches are in flight at once.
-int decode_queue_slot(int **slot)
+// Ring of ticket counters per device for the dynamic codeblock queue of the early-termination kernels.  A counter is
+// never reset: a launch draws exactly `tickets` tickets, so the host keeps the value every counter will have when the
+// next launch that draws it starts (launches that share a counter are serialised only if kSlots launches are in flight
+// at once).  Nothing here may run inside a stream capture (allocation, and a graph replay would reuse work_base):
+// capturing streams get no counter and the kernel uses its static stride.
+int decode_queue_slot(cudaStream_t s, unsigned tickets, unsigned **work, unsigned *work_base)
 {
     constexpr int kSlots = 4096, kMaxDev = 64;
     static std::mutex mu;
-    static int *ring[kMaxDev] = {};
+    static unsigned *ring[kMaxDev] = {};
+    static unsigned *base[kMaxDev] = {};
     static unsigned next[kMaxDev] = {};
+    *work = nullptr;
+    *work_base = 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); return NRLDPC_OK; }
+    if (cap != cudaStreamCaptureStatusNone) return NRLDPC_OK;
     int dev = 0;
     NRLDPC_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= kMaxDev) { *slot = nullptr; return NRLDPC_OK; }
+    if (dev < 0 || dev >= kMaxDev) return NRLDPC_OK;
     std::lock_guard<std::mutex> lock(mu);
     if (!ring[dev]) {
-        NRLDPC_CUDA(cudaMalloc(reinterpret_cast<void **>(&ring[dev]), kSlots * 2 * sizeof(int)));
-        NRLDPC_CUDA(cudaMemset(ring[dev], 0, kSlots * 2 * sizeof(int)));
+        unsigned *p = nullptr;
+        NRLDPC_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), kSlots * sizeof(unsigned)));
+        NRLDPC_CUDA(cudaMemset(p, 0, kSlots * sizeof(unsigned)));
+        ring[dev] = p;
+        base[dev] = new unsigned[kSlots]();
     }
-    *slot = ring[dev] + 2 * (next[dev]++ % kSlots);
+    const unsigned i = next[dev]++ % kSlots;
+    *work = ring[dev] + i;
+    *work_base = base[dev][i];
+    base[dev][i] += tickets;  // wraps like the device counter
     return NRLDPC_OK;
 }
 

@@ -111,9 +111,12 @@ constexpr int ils_of(int Zc)
     return -1;
 }
 
-template <int BGN, int ZC_> struct Code {
+// RR_: the kernel recovers its LLRs itself (rate recovery + HARQ combining fused into the LLR load, DecArgs::rr) and reads
+// them back from a row it wrote (coherent loads instead of the read-only path).
+template <int BGN, int ZC_, bool RR_ = false> struct Code {
     using G = Graph<BGN>;
     static constexpr int bgn = BGN, ZC = ZC_, iLS = ils_of(ZC_);
+    static constexpr bool RR = RR_;
     // Any lifting size >= 64: r-tile 0 must be full (it writes the 32 mirrored elements).  In a partial last
     // tile the lanes beyond Zc duplicate lane Zc-1 (same loads, same stores of the same values).
     static_assert(iLS >= 0 && ZC_ >= 64, "specialised kernels need a lifting size >= 64");
@@ -429,13 +432,20 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
     if (ET && (synd >> 31)) flag[0] = 1;
 }
 
+// A channel LLR: read-only path for the caller's llr[B,N]; L2-coherent load for a row this CTA recovered itself.
+template <class C> __device__ __forceinline__ float ld_llr(const float *p)
+{
+    if constexpr (C::RR) return __ldcg(p);
+    else return __ldg(p);
+}
+
 // Channel LLR of the degree-1 extension variable of row-block I (0 for the core rows), -0.0 -> +0.0.
 // (-0.0 -> +0.0 only when the syndrome reads the sign bit of LLR + Lr (ET); the messages do not depend on
 // the sign of a zero LLR: x = LLR + Lr and Lq = x - Lr give the same values either way.)
 template <class C, int I, bool ET> __device__ __forceinline__ float load_ext_llr(const Th<C> &th)
 {
     if constexpr (I >= 4) {
-        const float v = __ldg(th.llr + (C::kb + I - 2) * C::ZC);
+        const float v = ld_llr<C>(th.llr + (C::kb + I - 2) * C::ZC);
         return ET ? __fadd_rn(v, 0.0f) : v;
     } else return 0.f;
 }
@@ -526,7 +536,7 @@ __device__ __forceinline__ void vn_store_s(const Th<C> &th, const float lq)
 // (no -0.0 -> +0.0 here: the sum of the messages is never -0.0, so LLR + sum has the same value and sign.)
 template <class C, int J> __device__ __forceinline__ float load_col_llr(const Th<C> &th)
 {
-    if constexpr (J >= 2) return __ldg(th.llr + (J - 2) * C::ZC);
+    if constexpr (J >= 2) return ld_llr<C>(th.llr + (J - 2) * C::ZC);
     else return 0.f;
 }
 
@@ -684,6 +694,20 @@ __device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// Pull what codeblock cb will read into L2: its row of llr[B,N], or (fused rate recovery) its stretch of the received
+// sequence.  Thread 0 only.
+template <class C> __device__ __forceinline__ void prefetch_cb(const DecArgs &a, int cb)
+{
+    if constexpr (C::RR) {
+        const size_t esz = a.rr.in_f64 ? 8 : 4;
+        const uintptr_t p0 = reinterpret_cast<uintptr_t>(a.rr.src) + (size_t)a.rr.goff[cb] * esz;
+        const uintptr_t lo = p0 & ~(uintptr_t)15, hi = (p0 + (size_t)a.rr.E[cb] * esz) & ~(uintptr_t)15;
+        if (hi > lo) prefetch_l2(reinterpret_cast<const void *>(lo), (uint32_t)(hi - lo));
+    } else {
+        if ((reinterpret_cast<uintptr_t>(a.llr) & 15) == 0) prefetch_l2(a.llr + (size_t)cb * C::N, C::N * 4);  // 16-byte alignment
+    }
+}
+
 int num_sms()
 {
     static int n = 0;
@@ -737,8 +761,8 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     // blockIdx.x + gridDim.x, ...  The channel LLRs are read straight from global memory every iteration
     // (L2 hits); the NEXT codeblock's row is pulled into L2 while the current one is decoded, so that no
     // HBM latency is exposed at a codeblock boundary.
-    const bool pf = tid == 0 && (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0;  // bulk prefetch needs 16-byte alignment
-    if (pf) prefetch_l2(a.llr + (size_t)blockIdx.x * C::N, C::N * 4);
+    const bool pf = tid == 0;
+    if (pf) prefetch_cb<C>(a, blockIdx.x);
     // With early termination the codeblocks take different numbers of iterations, so the CTAs draw them from a
     // ticket counter (a.work) instead of a fixed stride: the first one is blockIdx.x, every further one
     // gridDim.x + ticket.  Thread 0 takes the ticket of the NEXT codeblock at the top (its latency hides behind the
@@ -746,11 +770,21 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     const bool dyn = ET && a.work != nullptr;
     for (int cb = blockIdx.x; cb < a.B; cb += gridDim.x) {
         int nx = 0;
-        if (ET) { if (dyn && tid == 0) nx = (int)gridDim.x + atomicAdd(a.work, 1); }
-        th.llr = a.llr + (size_t)cb * C::N + th.r;
+        if (ET) { if (dyn && tid == 0) nx = (int)gridDim.x + (int)(atomicAdd(a.work, 1u) - a.work_base); }
+        if constexpr (C::RR) {
+            // the LLR load is the rate recovery (+ HARQ combining) of this codeblock: received sequence -> this CTA's fp32
+            // row (L2-resident, rewritten for every codeblock) and the float64 soft buffer the caller keeps.  The codeblock
+            // state in shared memory is dead here, its first bytes serve the block reduction.
+            float *row = a.rr.scratch + (size_t)blockIdx.x * C::N;
+            rr_row(a.rr, cb, C::N, row, reinterpret_cast<double *>(smem));
+            __syncthreads();  // the row is read back by other threads, the reduction scratch is re-initialised below
+            th.llr = row + th.r;
+        } else {
+            th.llr = a.llr + (size_t)cb * C::N + th.r;
+        }
 #ifndef NRLDPC_EXP_NO_PF
         if (!dyn) {
-            if (pf && cb + (int)gridDim.x < a.B) prefetch_l2(a.llr + (size_t)(cb + gridDim.x) * C::N, C::N * 4);
+            if (pf && cb + (int)gridDim.x < a.B) prefetch_cb<C>(a, cb + (int)gridDim.x);
         }
 
 #endif
@@ -768,7 +802,7 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
 #ifdef NRLDPC_EXP_NO_INIT_LLR
                 const float v = 1.0f;
 #else
-                const float v = __fadd_rn(__ldg(th.llr + (j - 2) * ZC), 0.0f);  // -0.0 -> +0.0
+                const float v = __fadd_rn(ld_llr<C>(th.llr + (j - 2) * ZC), 0.0f);  // -0.0 -> +0.0
 #endif
                 float *dst = reinterpret_cast<float *>(smem + C::lq_base(j) + th.r4);
                 *dst = v;
@@ -778,7 +812,7 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
         if (ET) {
             if (dyn && tid == 0) {
                 s_next = nx;
-                if (pf && nx < a.B) prefetch_l2(a.llr + (size_t)nx * C::N, C::N * 4);
+                if (pf && nx < a.B) prefetch_cb<C>(a, nx);
             }
         }
         __syncthreads();
@@ -862,14 +896,6 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
         __syncthreads();  // the state is re-initialised for the next codeblock
         if (ET) { if (dyn) cb = nx - (int)gridDim.x; }  // the loop adds the stride back
     }
-    if (ET) {
-        // the last CTA to leave puts the queue slot back to zero for the next launch that draws it (every CTA has
-        // taken its last ticket before it counts itself out)
-        if (dyn && tid == 0) {
-            __threadfence();
-            if (atomicAdd(a.work + 1, 1) == (int)gridDim.x - 1) { a.work[0] = 0; a.work[1] = 0; }
-        }
-    }
 }
 
 template <class C>
@@ -887,17 +913,27 @@ int launch_spec(const DecArgs &a, int early_term, cudaStream_t s)
         }
         const int grid = std::min(a.B, C::ctas * num_sms());
         DecArgs b = a;
-        // dynamic codeblock queue of the early-termination kernels, once every CTA decodes several codeblocks: a
-        // {ticket, CTAs done} slot of a per-device ring that the kernel itself returns to zero (no allocation or memset on
-        // the launch path; NRLDPC_STATIC_QUEUE=1: fixed stride, for A/B timing)
+        // dynamic codeblock queue of the early-termination kernels, once every CTA decodes several codeblocks: a ticket
+        // counter from a per-device ring (no allocation or memset on the launch path; NRLDPC_STATIC_QUEUE=1 or a
+        // capturing stream: fixed stride)
         static const bool static_queue = getenv("NRLDPC_STATIC_QUEUE") != nullptr;
         if (early_term && a.B >= 2 * grid && !static_queue) {
-            if (int rc = decode_queue_slot(&b.work)) return rc;
+            if (int rc = decode_queue_slot(s, (unsigned)a.B, &b.work, &b.work_base)) return rc;
+        }
+        ScratchBuf rows;  // fused rate recovery: one fp32 row per persistent CTA, stream-ordered
+        if (b.rr.src && !b.rr.scratch) {
+            NRLDPC_CUDA(rows.alloc((size_t)grid * C::N * sizeof(float), s));
+            b.rr.scratch = rows.as<float>();
         }
         kern<<<grid, C::nwarps * 32, C::smem_bytes, s>>>(b);
         NRLDPC_CUDA(cudaGetLastError());
         return NRLDPC_OK;
     };
+    if (a.rr.src) {
+        using CR = Code<C::bgn, C::ZC, true>;
+        if (!early_term) { set_error("decode: the fused rate recovery runs with early termination only"); return NRLDPC_EINVAL; }
+        return a.beta == 0.f ? launch(decode_spec_kernel<CR, true, true>) : launch(decode_spec_kernel<CR, true, false>);
+    }
     if (a.beta == 0.f) return early_term ? launch(decode_spec_kernel<C, true, true>) : launch(decode_spec_kernel<C, false, true>);
     return early_term ? launch(decode_spec_kernel<C, true, false>) : launch(decode_spec_kernel<C, false, false>);
 }

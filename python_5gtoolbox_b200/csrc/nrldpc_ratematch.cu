@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "nrldpc_common.cuh"
+#include "nrldpc_raterecover.cuh"
 
 namespace nrldpc {
 namespace {
@@ -85,68 +86,20 @@ ratematch_kernel(const int8_t *__restrict__ dn, int N, int Ncb, int k0, int Qm, 
     }
 }
 
-// Number of filler positions met strictly before step t of the walk that starts at k0: the fillers are
-// the buffer positions [f0, f1) (py5gphy/ldpc/nr_ldpc_raterecover.py:34).
-__device__ __forceinline__ int fillers_before(int t, int k0, int f0, int f1, int Ncb)
-{
-    if (f1 <= f0) return 0;
-    auto overlap = [t](int a, int b) { return max(0, min(t, b) - a); };  // |[0,t) & [a,b)|, a >= 0
-    if (k0 <= f0) return overlap(f0 - k0, f1 - k0);
-    if (k0 >= f1) return overlap(f0 - k0 + Ncb, f1 - k0 + Ncb);
-    return overlap(0, f1 - k0) + overlap(f0 - k0 + Ncb, Ncb);
-}
-
-// De-interleaving + de-selection with averaging of repeated bits (:27-63): position pos of the circular
-// buffer, met at step t of the walk with `rank` non-filler positions before it, receives the received
-// values k = rank, rank + S, ... < E; the output is their float64 sum in that order divided by their
-// number (0 when there is none), the fillers get 10 * max|LLr_fe| (:30,:64), the rest of [0,N) is 0.
+// Rate recovery of codeblock blockIdx.x: the device function shared with the decoder kernels' fused LLR load
+// (nrldpc_raterecover.cuh).
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(kRmThreads)
 raterecover_kernel(const TIn *__restrict__ llr, int N, int Ncb, int k0, int Qm, int F0, int F1,
                    const int32_t *__restrict__ E_of, const long long *__restrict__ goff, TOut *__restrict__ outp)
 {
-    __shared__ double s_red[kRmThreads / 32];
-    __shared__ double s_max;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int E = E_of[b];
-    const TIn *fe = llr + goff[b];
+    __shared__ double s_red[33];
+    const int b = blockIdx.x;
     TOut *out = outp + (size_t)b * N;
-    // max |LLr_fe|
-    double m = 0.0;
-    for (int e = tid; e < E; e += kRmThreads) m = fmax(m, fabs((double)fe[e]));
-#pragma unroll
-    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) s_red[warp] = m;
-    __syncthreads();
-    if (tid == 0) {
-        double mm = 0.0;
-        for (int w = 0; w < kRmThreads / 32; ++w) mm = fmax(mm, s_red[w]);
-        s_max = mm * 10.0;
-    }
-    __syncthreads();
-    const double max_llr = s_max;
-    const int f0 = min(max(F0, 0), Ncb), f1 = min(max(F1, f0), Ncb);
-    const int S = Ncb - (f1 - f0);
-    const int cols = Qm > 0 ? E / Qm : 0;
-    for (int pos = tid; pos < N; pos += kRmThreads) {
-        double v = 0.0;
-        if (pos >= F0 && pos < F1) {
-            v = max_llr;
-        } else if (pos < Ncb && S > 0 && E > 0) {
-            int t = pos - k0;
-            if (t < 0) t += Ncb;
-            const int rank = t - fillers_before(t, k0, f0, f1, Ncb);
-            double sum = 0.0;
-            int cnt = 0;
-            for (int k = rank; k < E; k += S) {
-                const int q = k / cols, e = k - q * cols;
-                sum += (double)fe[(size_t)e * Qm + q];
-                ++cnt;
-            }
-            v = cnt ? sum / (double)cnt : 0.0;
-        }
-        out[pos] = (TOut)v;
-    }
+    if constexpr (sizeof(TOut) == 8)
+        rr_codeblock<TIn>(llr + goff[b], E_of[b], N, Ncb, k0, Qm, F0, F1, nullptr, reinterpret_cast<double *>(out), nullptr, s_red);
+    else
+        rr_codeblock<TIn>(llr + goff[b], E_of[b], N, Ncb, k0, Qm, F0, F1, nullptr, nullptr, reinterpret_cast<float *>(out), s_red);
 }
 
 // HARQ soft combining (py5gphy/nr_pdsch/nr_dlsch_decode.py:80-87): a zero on either side means "not

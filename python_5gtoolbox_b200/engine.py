@@ -428,3 +428,116 @@ def crc_check_device(blkandcrc, poly):
         _lib.check(_lib.lib().nrldpc_crc_check(blkandcrc.data_ptr(), B, n - _POLY_LEN[key], _POLY_ID[key], err.data_ptr(),
                                                _stream_ptr()), "crc_check")
     return err
+
+
+# ------------------------------------------------------------------ whole transport blocks (fused chain, host buffers)
+
+class _PinnedBlock:
+    """A block of the library's pinned host memory pool (nrldpc_host_alloc); returned to the pool when the last
+    NumPy view of it is garbage-collected."""
+    __slots__ = ("ptr", "nbytes", "__weakref__")
+
+    def __init__(self, nbytes):
+        p = ctypes.c_void_p()
+        _lib.check(_lib.lib().nrldpc_host_alloc(max(int(nbytes), 1), ctypes.byref(p)), "host_alloc")
+        self.ptr, self.nbytes = p.value, int(nbytes)
+
+    @property
+    def __array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            _lib.lib().nrldpc_host_free(self.ptr)
+        except Exception:   # interpreter shutdown
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """np.empty on pinned host memory from the library's pool: the host-buffer entry points DMA from / into it directly,
+    and the fused transport-block decoder stores its float64 soft buffer into it while it iterates."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    if n == 0:
+        return np.empty(shape, dtype)
+    return np.asarray(_PinnedBlock(n)).view(dtype).reshape(shape)
+
+
+def _llr_seq(x):
+    """The received sequence as the C ABI takes it: contiguous float32 or float64 (arithmetic is float64 either way)."""
+    x = np.asarray(x).reshape(-1)
+    return np.ascontiguousarray(x, np.float32 if x.dtype == np.float32 else np.float64)
+
+
+def sch_decode_host(llr_g, E_list, bgn, Zc, Ncb, k0, Qm, K_apo, A, L, alpha, beta, cur=None, want_soft=True):
+    """Rate recovery + HARQ combining + min-sum decoding + CB/TB CRC of one transport block in two launches
+    (nrldpc_sch_decode_host; py5gphy/nr_pdsch/nr_dlsch_decode.py:56-107).  NumPy in / out.
+    Returns dict(tbblk int8[A], tb_err int, cb_err uint8[C], status bool[C], iters int32[C], soft float64[C,N] | None)."""
+    E = np.ascontiguousarray(E_list, np.int32).reshape(-1)
+    C = E.size
+    K, N, Nf, M = dims(bgn, Zc)
+    x = _llr_seq(llr_g)
+    assert x.size == int(E.sum(dtype=np.int64))
+    if cur is not None:
+        cur = np.ascontiguousarray(cur, np.float64)
+        assert cur.shape == (C, N)
+    soft = pinned_empty((C, N), np.float64) if want_soft else None
+    tbblk = pinned_empty((A,), np.int8)
+    small = np.empty(1 + 2 * C, np.uint8)
+    iters = np.empty(C, np.int32)
+    _lib.check(_lib.lib().nrldpc_sch_decode_host(
+        x.ctypes.data, int(x.dtype == np.float64), C, bgn, int(Zc), int(Ncb), int(k0), int(Qm), int(K_apo), E.ctypes.data,
+        cur.ctypes.data if cur is not None else None, soft.ctypes.data if soft is not None else None, int(L), float(alpha),
+        float(beta), int(A), tbblk.ctypes.data, small.ctypes.data, small.ctypes.data + 1, small.ctypes.data + 1 + C,
+        iters.ctypes.data), "sch_decode")
+    return dict(tbblk=tbblk, tb_err=int(small[0]), cb_err=small[1:1 + C], status=small[1 + C:].astype(bool), iters=iters, soft=soft)
+
+
+def sch_recover_host(llr_g, E_list, bgn, Zc, Ncb, k0, Qm, K_apo, cur=None):
+    """Rate recovery + HARQ combining of a transport block's codeblocks -> float64 [C,N] (new_LLr_dns)."""
+    E = np.ascontiguousarray(E_list, np.int32).reshape(-1)
+    C = E.size
+    K, N, Nf, M = dims(bgn, Zc)
+    x = _llr_seq(llr_g)
+    assert x.size == int(E.sum(dtype=np.int64))
+    if cur is not None:
+        cur = np.ascontiguousarray(cur, np.float64)
+        assert cur.shape == (C, N)
+    soft = pinned_empty((C, N), np.float64)
+    _lib.check(_lib.lib().nrldpc_sch_recover_host(x.ctypes.data, int(x.dtype == np.float64), C, N, int(Ncb), int(k0), int(Qm), int(Zc),
+                                                  int(K_apo), K, E.ctypes.data, cur.ctypes.data if cur is not None else None,
+                                                  soft.ctypes.data), "sch_recover")
+    return soft
+
+
+def sch_segment_host(trblk, C, K):
+    """TB CRC attachment + code block segmentation + CB CRC: int8 [A] -> cbs int8 [C,K] with -1 fillers
+    (py5gphy/nr_pdsch/nr_dlsch.py:29-46, py5gphy/ldpc/nr_ldpc_cbsegment.py:7-33)."""
+    t = np.ascontiguousarray(trblk, np.int8).reshape(-1)
+    cbs = np.empty((C, K), np.int8)
+    _lib.check(_lib.lib().nrldpc_sch_segment_host(t.ctypes.data, t.size, int(C), int(K), cbs.ctypes.data), "sch_segment")
+    return cbs
+
+
+def encode_ratematch_host(cbs, bgn, Zc, Ncb, k0, Qm, E_list, fix_fillers=True):
+    """LDPC encoding + rate matching + concatenation of a transport block's codeblocks: cbs int8 [C,K] (fillers -1,
+    set to 0 in place when fix_fillers, like encode_ldpc) -> int8 [sum E]."""
+    E = np.ascontiguousarray(E_list, np.int32).reshape(-1)
+    assert cbs.dtype == np.int8 and cbs.flags.c_contiguous and cbs.ndim == 2 and cbs.shape[0] == E.size
+    K, N, Nf, M = dims(bgn, Zc)
+    assert cbs.shape[1] == K
+    g = np.empty(int(E.sum(dtype=np.int64)), np.int8)
+    _lib.check(_lib.lib().nrldpc_encode_ratematch_host(cbs.ctypes.data, E.size, bgn, int(Zc), int(bool(fix_fillers)), int(Ncb), int(k0),
+                                                       int(Qm), E.ctypes.data, g.ctypes.data), "encode_ratematch")
+    return g
+
+
+def sch_encode_host(trblk, C, bgn, Zc, Ncb, k0, Qm, E_list):
+    """TB CRC + segmentation + LDPC encoding + rate matching + concatenation, device-resident in between:
+    trblk int8 [A] -> int8 [sum E] (py5gphy/nr_pdsch/nr_dlsch.py:12-74)."""
+    E = np.ascontiguousarray(E_list, np.int32).reshape(-1)
+    t = np.ascontiguousarray(trblk, np.int8).reshape(-1)
+    g = np.empty(int(E.sum(dtype=np.int64)), np.int8)
+    _lib.check(_lib.lib().nrldpc_sch_encode_host(t.ctypes.data, t.size, int(C), bgn, int(Zc), int(Ncb), int(k0), int(Qm),
+                                                 E.ctypes.data, g.ctypes.data), "sch_encode")
+    return g

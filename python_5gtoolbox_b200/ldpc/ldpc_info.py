@@ -81,6 +81,10 @@ def getH(Zc, bgn, iLS):
     H = H.view(TaggedH)
     if find_iLS(Zc) == iLS:
         H.nrldpc_tag = (bgn, Zc)
+        # the tag routes decode_ldpc / ldpc_decoder_BF to the quasi-cyclic kernels, which never look at the entries:
+        # the tagged matrix is read-only so that it cannot drift away from its tag (an in-place edit raises; edit a
+        # .copy(), which carries no tag and is decoded entry by entry on the generic kernels)
+        H.flags.writeable = False
     return H
 
 

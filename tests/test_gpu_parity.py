@@ -341,7 +341,12 @@ def test_decode_headline_roundtrip_device(eng):
     assert torch.equal(r["ck"][st], cw[st])
     assert int(r["iters"].min()) >= 1 and int(r["iters"].max()) <= 10
     cnt = eng.count_errors(ck, r["ck"], K, r["iters"])
-    assert cnt.tolist()[0] == B and cnt.tolist()[1] == int((~st).sum()) or cnt.tolist()[1] <= int((~st).sum())
+    cnt = cnt.tolist()
+    assert cnt[0] == B                                 # codeblocks counted
+    assert cnt[1] <= int((~st).sum())                  # a block error implies a failed parity check (not the converse)
+    info_err = (r["ck"][:, :K] != ck).any(1)
+    assert cnt[1] == int(info_err.sum()) and cnt[2] == int((r["ck"][:, :K] != ck).sum())
+    assert cnt[3] == int(r["iters"].sum())
     # throughput mode (no early exit) reaches the same codewords on the converged blocks
     r2 = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, False)
     assert int(r2["iters"].min()) == 10

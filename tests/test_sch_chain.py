@@ -186,3 +186,216 @@ def test_sch_chain_golden(eng, sch_golden):
             else:   # a failed block: fp32 vs the reference's float64 may differ in a few of the wrong bits
                 assert np.mean(tb != d[f"tbblk_{t}"]) < 0.02, (name, t)
             cur = new
+
+
+# ------------------------------------------------------------------ the fused transport-block entry points (round 2)
+
+def _tb_case(rng, bgn, Zc, C, Qm, NL, rv, ncb_frac, rate_scale, F):
+    """A synthetic transport block laid out like get_cbs_info would: C codeblocks of cbz payload bits."""
+    from python_5gtoolbox_b200.ldpc import nr_ldpc_ratematch as RM
+    K, N = ((22, 66) if bgn == 1 else (10, 50))
+    K, N = K * Zc, N * Zc
+    Lcb = 24 if C > 1 else 0
+    K_apo = K - F
+    cbz = K_apo - Lcb
+    B = C * cbz
+    Ltb = 24 if B - 24 > 3824 else 16
+    A = B - Ltb
+    assert (A > 3824) == (Ltb == 24)
+    Ncb = N if ncb_frac == 1.0 else int(N * ncb_frac)
+    k0 = RM.get_k0(Ncb, bgn, rv, Zc)
+    G = int(C * N * rate_scale) // (Qm * NL) * (Qm * NL) + Qm * NL * (C // 2)
+    Er = RM.get_Er_ldpc(G, C, Qm, NL)
+    return dict(bgn=bgn, Zc=Zc, C=C, Qm=Qm, K=K, N=N, K_apo=K_apo, cbz=cbz, A=A, Ltb=Ltb, Ncb=Ncb, k0=k0, Er=Er, G=G)
+
+
+_TB_CASES = [  # bgn, Zc, C, Qm, NL, rv, Ncb fraction, E/N scale, fillers
+    (1, 384, 5, 8, 4, 0, 1.0, 0.40, 16),      # specialised kernel, high rate, fillers
+    (1, 384, 3, 2, 1, 2, 0.85, 1.30, 0),      # LBRM + repetition (E > Ncb)
+    (1, 208, 4, 6, 1, 0, 1.0, 0.55, 40),      # specialised kernel, 16 * odd lifting size
+    (2, 144, 2, 4, 2, 1, 1.0, 0.70, 8),       # BG2 specialised
+    (2, 64, 6, 2, 2, 3, 0.9, 0.60, 20),       # table-driven kernel, several codeblocks per CTA
+    (1, 12, 9, 1, 1, 0, 1.0, 0.90, 3),        # Zc < 32: several codeblocks per warp; Qm = 1
+    (2, 10, 1, 2, 1, 0, 1.0, 1.00, 5),        # single codeblock: no CB CRC, 16-bit TB CRC
+]
+
+
+def _make_tb(eng, oracle, rng, t, snr_db, first=None):
+    """Random transport block -> (trblk, g, llr float32).  Encoded by the oracle-checked chain of engine calls."""
+    from python_5gtoolbox_b200 import crc
+    trblk = rng.integers(0, 2, t["A"]).astype("i1") if first is None else first
+    blk = crc.nr_crc_encode(trblk, '24A' if t["Ltb"] == 24 else '16')
+    cbs = np.full((t["C"], t["K"]), -1, "i1")
+    if t["C"] == 1:
+        cbs[0, :t["cbz"]] = blk
+    else:
+        cbs[:, :t["K_apo"]] = crc.nr_crc_encode_batch(blk.reshape(t["C"], t["cbz"]), '24B')
+    dn = eng.encode_batch(cbs.copy(), t["bgn"], t["Zc"])
+    g = np.concatenate([oracle.ratematch_ldpc(dn[c], t["Ncb"], t["Er"][c], t["k0"], t["Qm"]) for c in range(t["C"])])
+    sigma = 10 ** (-snr_db / 20)
+    llr = (2 * ((1 - 2 * g.astype("f8")) + rng.normal(0, sigma, g.size)) / sigma ** 2).astype("f4")
+    return trblk, cbs, g, llr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _TB_CASES)
+def test_fused_sch_decode_equals_staged_chain(eng, oracle, case):
+    """nrldpc_sch_decode_host (rate recovery + HARQ combining inside the decoder's LLR load, CB/TB CRC kernel) against
+    the same chain done stage by stage: oracle rate recovery / combining (float64-exact), the fp32 decoder on the
+    rounded soft buffer, oracle CRCs."""
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    t = _tb_case(rng, *case)
+    bgn, Zc, C, N, K = t["bgn"], t["Zc"], t["C"], t["N"], t["K"]
+    snr = 6.0 if t["Qm"] >= 6 and case[7] < 0.5 else 2.0
+    trblk, cbs, g, llr = _make_tb(eng, oracle, rng, t, snr)
+    off = np.concatenate([[0], np.cumsum(t["Er"])])
+    cur = None
+    for tx, dt in enumerate((np.float32, np.float64, np.float32)):   # 1st tx, then two HARQ combinations
+        x = llr.astype(dt) * (1.0 if tx == 0 else rng.uniform(0.5, 1.5))
+        want = np.stack([oracle.raterecover_ldpc(x[off[c]:off[c + 1]].astype(np.float64), t["Ncb"], N, t["k0"], t["Qm"], Zc,
+                                                 t["K_apo"], K) for c in range(C)])
+        if cur is not None:
+            want = oracle.harq_combine(want, cur)
+        r = eng.sch_decode_host(x, t["Er"], bgn, Zc, t["Ncb"], t["k0"], t["Qm"], t["K_apo"], t["A"], 12, 0.8, 0.1, cur=cur)
+        assert r["soft"].dtype == np.float64 and np.array_equal(r["soft"], want), (case, tx)      # float64-exact
+        d = eng.decode_batch(want.astype(np.float32), Zc, bgn, 12, 0.8, 0.1, True)
+        assert np.array_equal(r["status"], d["status"]) and np.array_equal(r["iters"], d["iters"]), (case, tx)
+        tb = d["ck"][:, :t["cbz"]].reshape(-1)
+        assert np.array_equal(r["tbblk"], tb[:t["A"]]), (case, tx)
+        _, tb_err = oracle.crc_decode(tb, '24A' if t["Ltb"] == 24 else '16')
+        assert r["tb_err"] == tb_err, (case, tx)
+        if C > 1:
+            cb_err = [oracle.crc_decode(d["ck"][c, :t["K_apo"]], '24B')[1] for c in range(C)]
+            assert r["cb_err"].tolist() == cb_err, (case, tx)
+        else:
+            assert r["cb_err"].tolist() == [0]
+        if tx == 0:
+            assert r["tb_err"] == 0 and np.array_equal(r["tbblk"], trblk), case   # a clean first transmission decodes
+            soft_sep = eng.sch_recover_host(x, t["Er"], bgn, Zc, t["Ncb"], t["k0"], t["Qm"], t["K_apo"])
+            assert np.array_equal(soft_sep, want)
+        else:
+            assert np.array_equal(eng.sch_recover_host(x, t["Er"], bgn, Zc, t["Ncb"], t["k0"], t["Qm"], t["K_apo"], cur=cur), want)
+        cur = np.array(want)   # pageable copy: the next call stages it through the pinned ring
+    # a corrupted codeblock: TB CRC and that codeblock's CRC fail, the others stay clean
+    bad = llr.copy()
+    bad[off[C - 1]:off[C]] = rng.normal(0, 1, t["Er"][C - 1])
+    r = eng.sch_decode_host(bad, t["Er"], bgn, Zc, t["Ncb"], t["k0"], t["Qm"], t["K_apo"], t["A"], 4, 0.8, 0.0)
+    assert r["tb_err"] == 1 and not r["status"][C - 1]
+    if C > 1:
+        assert r["cb_err"][C - 1] == 1 and not r["cb_err"][:C - 1].any()
+
+
+@pytest.mark.gpu
+def test_fused_sch_decode_device_entry(eng, oracle):
+    """nrldpc_sch_decode on device buffers and a caller's stream, ck handed back."""
+    import ctypes
+    import torch
+    from python_5gtoolbox_b200 import _lib
+    rng = np.random.default_rng(12)
+    t = _tb_case(rng, 1, 384, 4, 4, 2, 0, 1.0, 0.5, 24)
+    trblk, cbs, g, llr = _make_tb(eng, oracle, rng, t, 3.0)
+    C, N, Nf = t["C"], t["N"], t["N"] + 2 * t["Zc"]
+    dev = torch.device("cuda")
+    E = torch.tensor(t["Er"], dtype=torch.int32, device=dev)
+    goff = torch.tensor(np.concatenate([[0], np.cumsum(t["Er"])[:-1]]), dtype=torch.int64, device=dev)
+    x = torch.from_numpy(llr).to(dev)
+    soft = torch.empty((C, N), dtype=torch.float64, device=dev)
+    ck = torch.empty((C, Nf), dtype=torch.int8, device=dev)
+    tb = torch.empty(t["A"], dtype=torch.int8, device=dev)
+    flags = torch.full((1 + 2 * C,), 7, dtype=torch.uint8, device=dev)
+    iters = torch.empty(C, dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        _lib.check(_lib.lib().nrldpc_sch_decode(x.data_ptr(), 0, C, 1, 384, t["Ncb"], t["k0"], t["Qm"], t["K_apo"], E.data_ptr(),
+                                                goff.data_ptr(), None, soft.data_ptr(), 10, 0.8, 0.0, t["A"], ck.data_ptr(),
+                                                tb.data_ptr(), flags.data_ptr(), flags.data_ptr() + 1, flags.data_ptr() + 1 + C,
+                                                iters.data_ptr(), ctypes.c_void_p(st.cuda_stream)), "sch_decode")
+    st.synchronize()
+    assert flags[0].item() == 0 and np.array_equal(tb.cpu().numpy(), trblk)
+    assert not flags[1:1 + C].any() and flags[1 + C:].all()
+    want = eng.raterecover_batch(llr, t["Er"], t["Ncb"], N, t["k0"], t["Qm"], 384, t["K_apo"], t["K"], out_f64=True)
+    assert np.array_equal(soft.cpu().numpy(), want)
+    assert np.array_equal(ck.cpu().numpy()[:, :t["K_apo"]], cbs[:, :t["K_apo"]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _TB_CASES)
+def test_fused_sch_encode_equals_staged_chain(eng, oracle, case):
+    rng = np.random.default_rng(7 + (hash(case) & 0xfff))
+    t = _tb_case(rng, *case)
+    trblk, cbs, g, _ = _make_tb(eng, oracle, rng, t, 5.0)
+    seg = eng.sch_segment_host(trblk, t["C"], t["K"])
+    assert seg.dtype == np.int8 and np.array_equal(seg, cbs), case                      # TB CRC + segmentation + CB CRC
+    work = cbs.copy()
+    g2 = eng.encode_ratematch_host(work, t["bgn"], t["Zc"], t["Ncb"], t["k0"], t["Qm"], t["Er"])
+    assert np.array_equal(g2, g), case
+    fixed = cbs.copy()
+    fixed[:, 2 * t["Zc"]:][fixed[:, 2 * t["Zc"]:] == -1] = 0
+    assert np.array_equal(work, fixed), case                                            # encode_ldpc's in-place side effect
+    g3 = eng.sch_encode_host(trblk, t["C"], t["bgn"], t["Zc"], t["Ncb"], t["k0"], t["Qm"], t["Er"])
+    assert np.array_equal(g3, g), case
+    with pytest.raises(AssertionError):                                                  # crc.nr_crc_encode asserts 0/1 input (:18-20)
+        bad = trblk.copy()
+        bad[t["A"] // 2] = 2
+        eng.sch_encode_host(bad, t["C"], t["bgn"], t["Zc"], t["Ncb"], t["k0"], t["Qm"], t["Er"])
+
+
+@pytest.mark.gpu
+def test_pinned_pool_and_pageable_host_path(eng):
+    """Pinned blocks are recycled; the host-buffer decoder gives the same results from pageable NumPy memory (staged by
+    the copy threads) as from pinned memory, also for batches of several pipeline chunks."""
+    a = eng.pinned_empty((3, 1000), np.float64)
+    p = a.ctypes.data
+    a[:] = 1.5
+    del a
+    b = eng.pinned_empty((3000,), np.float64)
+    assert b.ctypes.data == p                      # same size class -> the block came back from the pool
+    import torch
+    bgn, Zc, B = 1, 384, 700                       # 700 codeblocks = 71 MB of LLRs: three 32 MiB pipeline chunks
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    ck = eng.random_bits(B, K, seed=5, device="cuda")
+    dn = eng.encode_batch(ck, bgn)
+    llr_d = eng.awgn_llr(dn, 1.0, seed=6)
+    llr = llr_d.cpu().numpy()                      # pageable
+    pin = eng.pinned_empty(llr.shape, np.float32)
+    pin[...] = llr
+    r_dev = eng.decode_batch(llr_d, Zc, bgn, 10, 0.8, 0.0, True, want_info=True)
+    for src in (llr, pin):
+        r = eng.decode_batch(src, Zc, bgn, 10, 0.8, 0.0, True, want_info=True)
+        assert np.array_equal(r["ck"], r_dev["ck"].cpu().numpy())
+        assert np.array_equal(r["info"].view(np.int32), r_dev["info"].cpu().numpy())
+        assert np.array_equal(r["iters"], r_dev["iters"].cpu().numpy())
+        assert np.array_equal(r["status"], r_dev["status"].cpu().numpy().astype(bool))
+
+
+@pytest.mark.gpu
+def test_early_termination_queue_under_graph_capture(eng):
+    """The dynamic codeblock queue of the early-termination kernels keeps host-side state per launch: a launch captured
+    into a CUDA graph must not use it (a replay would reuse the ticket base).  Replays and interleaved eager launches
+    give the eager results."""
+    import torch
+    bgn, Zc, B = 1, 384, 600                      # > 2 x 148 codeblocks: the eager launch uses the ticket queue
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    ck = eng.random_bits(B, K, seed=9, device="cuda")
+    llr = eng.awgn_llr(eng.encode_batch(ck, bgn), 0.7, seed=10)
+    ref = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, True)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, True)   # warm-up outside the capture (function attributes)
+        st.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            out = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, True)
+    for rep in range(3):
+        for k in out:
+            if out[k] is not None:
+                out[k].fill_(3)
+        g.replay()
+        eager = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, True)   # shares the device with the replay
+        torch.cuda.synchronize()
+        for k in ("ck", "status", "iters"):
+            assert torch.equal(out[k], ref[k]), (rep, k)
+            assert torch.equal(eager[k], ref[k]), (rep, k)

@@ -25,14 +25,29 @@ for name, A, R, Qm, NL, G in cases:
     sigma = 10 ** (-(6.5 if Qm == 8 else 0.0) / 20)
     llr = (2 * ((1 - 2 * g.astype("f4")) + rng.normal(0, sigma, G).astype("f4")) / sigma ** 2).astype("f4")
     nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, 0, TBS_LBRM, cfg)
+    nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, 0, TBS_LBRM, cfg)
+    reps = 20
     t0 = time.perf_counter()
-    for _ in range(3):
+    for _ in range(reps):
         st, tb, new = nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, 0, TBS_LBRM, cfg)
-    t_dec = (time.perf_counter() - t0) / 3
+    t_dec = (time.perf_counter() - t0) / reps
+    llr64 = llr.astype("f8")   # what the reference's receive chain hands over (float32 values in a float64 array)
+    nr_dlsch_decode.DLSCHDecode(llr64, A, Qm, R, NL, 0, TBS_LBRM, cfg)
     t0 = time.perf_counter()
-    g2 = nr_dlsch.DLSCHEncode(trblk, A, Qm, R, NL, 0, TBS_LBRM, G)
-    t_enc2 = time.perf_counter() - t0
+    for _ in range(reps):
+        st64, tb64, new64 = nr_dlsch_decode.DLSCHDecode(llr64, A, Qm, R, NL, 0, TBS_LBRM, cfg)
+    t_dec64 = (time.perf_counter() - t0) / reps
+    assert st64 == st and np.array_equal(tb64, tb) and np.array_equal(new64, new)
+    t0 = time.perf_counter()
+    for _ in range(reps):   # retransmission: HARQ combining with the soft buffer of the previous call
+        st2, tb2, new2 = nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, 0, TBS_LBRM, cfg, HARQ_on=True, current_LLr_dns=new)
+    t_harq = (time.perf_counter() - t0) / reps
+    print(f"   float64 LLRs in: {t_dec64 * 1e3:.2f} ms; with HARQ combining (soft buffer in and out): {t_harq * 1e3:.2f} ms")
+    t0 = time.perf_counter()
+    for _ in range(10):
+        g2 = nr_dlsch.DLSCHEncode(trblk, A, Qm, R, NL, 0, TBS_LBRM, G)
+    t_enc2 = (time.perf_counter() - t0) / 10
     assert np.array_equal(g, g2)
-    print(f"{name}: TBS={A} G={G} C x N = {new.shape}  DLSCHEncode {t_enc2 * 1e3:.1f} ms (first call {t_enc * 1e3:.0f} ms)  "
-          f"DLSCHDecode {t_dec * 1e3:.1f} ms  -> {A / t_dec / 1e9:.3f} Gbit/s of transport-block bits  status={st} ok={np.array_equal(tb, trblk)}")
+    print(f"{name}: TBS={A} G={G} C x N = {new.shape}  DLSCHEncode {t_enc2 * 1e3:.2f} ms (first call {t_enc * 1e3:.0f} ms)  "
+          f"DLSCHDecode {t_dec * 1e3:.2f} ms  -> {A / t_dec / 1e9:.3f} Gbit/s of transport-block bits  status={st} ok={np.array_equal(tb, trblk)}")
     assert st and np.array_equal(tb, trblk)
