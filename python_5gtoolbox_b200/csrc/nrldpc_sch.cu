@@ -8,10 +8,13 @@
 // float64 soft buffer the caller keeps for HARQ is written by the decoder's prologue; when the caller's buffer is
 // pinned host memory the kernel stores straight into it over PCIe while the iterations run (no D2H copy).
 // Transmit side: TB CRC + segmentation + CB CRC in two small kernels, then the encoder and the rate matcher.
+#include <immintrin.h>
 #include <sched.h>
 
 #include <algorithm>
 #include <array>
+#include <chrono>
+#include <cstdio>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -92,6 +95,32 @@ PinnedPool &pinned_pool()
     return *p;
 }
 
+// memcpy with non-temporal stores (AVX2) for the large pageable -> pinned copies: the destination is read next by the DMA
+// engine, not by this core, so it should neither be fetched for ownership nor evict the caller's working set.
+__attribute__((target("avx2"))) void copy_nt_avx2(char *dst, const char *src, size_t n)
+{
+    while (n && (reinterpret_cast<uintptr_t>(dst) & 31)) { *dst++ = *src++; --n; }
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+    }
+    _mm_sfence();
+    if (i < n) memcpy(dst + i, src + i, n - i);
+}
+void copy_piece(void *dst, const void *src, size_t n)
+{
+    static const bool nt = __builtin_cpu_supports("avx2") && !(getenv("NRLDPC_COPY_NT") && atoi(getenv("NRLDPC_COPY_NT")) == 0);
+    if (nt && n >= ((size_t)64 << 10)) copy_nt_avx2((char *)dst, (const char *)src, n);
+    else memcpy(dst, src, n);
+}
+
 // Host threads that copy between pageable and pinned memory (a single core moves ~10 GB/s, a PCIe 5 x16 link 55).
 struct CopyThreads {
     struct Job { char *dst; const char *src; size_t n; };
@@ -104,7 +133,7 @@ struct CopyThreads {
     CopyThreads()
     {
         // helpers = this process's share of the cores it may run on, minus the calling thread (torchrun exports the
-        // number of ranks on the node), at most 7
+        // number of ranks on the node), at most 11 (measured on a 16-core B200 host: 3 helpers 34 GB/s, 7 44 GB/s, 11 46 GB/s, 15 44 GB/s)
         int n = 3;
         if (const char *e = getenv("NRLDPC_COPY_THREADS")) n = atoi(e);
         else {
@@ -113,7 +142,7 @@ struct CopyThreads {
             if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
             int ranks = 1;
             if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
-            n = std::max(0, std::min(cores / ranks - 1, 7));
+            n = std::max(0, std::min(cores / ranks - 1, 11));
         }
         nthreads = std::max(0, std::min(n, 15));
         for (int i = 0; i < nthreads; ++i) th.emplace_back([this] { loop(); });
@@ -129,7 +158,7 @@ struct CopyThreads {
                 j = q.front();
                 q.pop_front();
             }
-            memcpy(j.dst, j.src, j.n);
+            copy_piece(j.dst, j.src, j.n);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 if (--pending == 0) cv_done.notify_all();
@@ -141,7 +170,7 @@ struct CopyThreads {
     {
         constexpr size_t kMin = (size_t)256 << 10;
         const int parts = (int)std::min<size_t>((size_t)nthreads + 1, std::max<size_t>(1, n / kMin));
-        if (parts <= 1) { memcpy(dst, src, n); return; }
+        if (parts <= 1) { copy_piece(dst, src, n); return; }
         const size_t per = ((n + parts - 1) / parts + 63) & ~(size_t)63;
         {
             std::lock_guard<std::mutex> lk(mu);
@@ -153,7 +182,7 @@ struct CopyThreads {
             }
         }
         cv.notify_all();
-        memcpy(dst, src, std::min(per, n));
+        copy_piece(dst, src, std::min(per, n));
         std::unique_lock<std::mutex> lk(mu);
         cv_done.wait(lk, [this] { return pending == 0; });
     }
@@ -177,7 +206,7 @@ void host_copy(void *dst, const void *src, size_t n)
 // Per-device ring of pinned staging slots for pageable caller memory.
 struct StageRing {
     static constexpr int kSlots = 4;
-    static constexpr size_t kSlotBytes = (size_t)8 << 20;
+    size_t kSlotBytes = (size_t)8 << 20;
     void *slot[kSlots] = {};
     cudaEvent_t ev[kSlots] = {};
     int next = 0;
@@ -185,6 +214,7 @@ struct StageRing {
     int init()
     {
         if (slot[0]) return NRLDPC_OK;
+        if (const char *e = getenv("NRLDPC_STAGE_MB")) kSlotBytes = (size_t)std::max(1, atoi(e)) << 20;
         for (int i = 0; i < kSlots; ++i) {
             NRLDPC_CUDA(cudaHostAlloc(&slot[i], kSlotBytes, cudaHostAllocPortable));
             NRLDPC_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
@@ -217,8 +247,8 @@ int h2d_async(void *dst, const void *src, size_t n, cudaStream_t s)
     StageRing &R = stage_ring();
     std::lock_guard<std::mutex> lk(R.mu);
     if (int rc = R.init()) return rc;
-    for (size_t o = 0; o < n; o += StageRing::kSlotBytes) {
-        const size_t m = std::min(StageRing::kSlotBytes, n - o);
+    for (size_t o = 0; o < n; o += R.kSlotBytes) {
+        const size_t m = std::min(R.kSlotBytes, n - o);
         const int i = R.next++ % StageRing::kSlots;
         NRLDPC_CUDA(cudaEventSynchronize(R.ev[i]));  // the slot's previous DMA is done
         host_copy(R.slot[i], (const char *)src + o, m);
@@ -243,8 +273,8 @@ int d2h_sync(void *dst, const void *src, size_t n, cudaStream_t s)
     // DMA of chunk i+1 overlaps the host copy of chunk i
     size_t o_prev = 0, m_prev = 0;
     int i_prev = -1;
-    for (size_t o = 0; o < n; o += StageRing::kSlotBytes) {
-        const size_t m = std::min(StageRing::kSlotBytes, n - o);
+    for (size_t o = 0; o < n; o += R.kSlotBytes) {
+        const size_t m = std::min(R.kSlotBytes, n - o);
         const int i = R.next++ % StageRing::kSlots;
         NRLDPC_CUDA(cudaEventSynchronize(R.ev[i]));
         NRLDPC_CUDA(cudaMemcpyAsync(R.slot[i], (const char *)src + o, m, cudaMemcpyDeviceToHost, s));
@@ -642,6 +672,17 @@ extern "C" int nrldpc_sch_decode_host(const void *llr_g, int in_f64, int C, int 
     if (int rc = host_offsets("sch_decode", E, C, Qm, &off, &total)) return rc;
     cudaStream_t s;
     if (int rc = host_stream(&s)) return rc;
+    // NRLDPC_TRACE=1: host clock at every stage boundary (=2: with a stream synchronisation in front, so that the
+    // device time of a stage is attributed to it); timing aid only
+    static const int trace = getenv("NRLDPC_TRACE") ? atoi(getenv("NRLDPC_TRACE")) : 0;
+    double tt[10] = {};
+    int nt = 0;
+    auto mark = [&]() {
+        if (!trace || nt >= 10) return;
+        if (trace > 1) cudaStreamSynchronize(s);
+        tt[nt++] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    mark();
     const size_t esz = in_f64 ? 8 : 4, nsoft = (size_t)C * d.N * 8;
     // small results in one block: tb_err | cb_err[C] | status[C] | iters[C], each part 16-byte aligned
     const size_t o_cb = 16, o_st = o_cb + (((size_t)C + 15) & ~(size_t)15), o_it = o_st + (((size_t)C + 15) & ~(size_t)15);
@@ -668,15 +709,18 @@ extern "C" int nrldpc_sch_decode_host(const void *llr_g, int in_f64, int C, int 
         }
     }
     if (cur) NRLDPC_CUDA(d_cur.alloc(nsoft, s));
+    mark();
     if (int rc = h2d_async(d_E.p, E, (size_t)C * 4, s)) return rc;
     if (int rc = h2d_async(d_off.p, off.data(), (size_t)C * 8, s)) return rc;
     if (int rc = h2d_async(d_in.p, llr_g, (size_t)total * esz, s)) return rc;
     if (cur) if (int rc = h2d_async(d_cur.p, cur, nsoft, s)) return rc;
+    mark();
     uint8_t *sm = d_small.as<uint8_t>();
     int rc = nrldpc_sch_decode(d_in.p, in_f64, C, bgn, Zc, Ncb, k0, Qm, K_apo, d_E.as<int32_t>(), d_off.as<long long>(),
                                cur ? d_cur.as<double>() : nullptr, soft_dev, max_iter, alpha, beta, A, nullptr, d_tb.as<int8_t>(), sm,
                                sm + o_cb, sm + o_st, reinterpret_cast<int32_t *>(sm + o_it), s);
     if (rc != NRLDPC_OK) { cudaStreamSynchronize(s); return rc; }
+    mark();
     void *h_small = nullptr;
     NRLDPC_CUDA(pinned_pool().get(nsmall, &h_small));
     cudaError_t e = cudaMemcpyAsync(h_small, sm, nsmall, cudaMemcpyDeviceToHost, s);
@@ -694,6 +738,10 @@ extern "C" int nrldpc_sch_decode_host(const void *llr_g, int in_f64, int C, int 
         if (iters) memcpy(iters, h + o_it, (size_t)C * 4);
     }
     pinned_pool().put(h_small);
+    mark();
+    if (trace && nt == 5)
+        fprintf(stderr, "nrldpc trace sch_decode_host C=%d: setup %.0f us, h2d %.0f us, launches %.0f us, d2h+sync %.0f us (soft %s)\n", C,
+                tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3], soft ? (soft_copy ? "copied" : "zero-copy") : "none");
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(results)");
     return rc;
 }
