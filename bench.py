@@ -82,7 +82,7 @@ def cpu_reference_run(steps, warmup, sample_cbs=None, early_term=0):
     O.build()
     O.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     threads = O.num_threads()
-    n = sample_cbs or max(threads * 100, 64)   # ~26 ms per codeblock per core -> a few seconds per step
+    n = sample_cbs or max(threads * 100, 64)   # ~13-15 ms per codeblock per core -> 1-2 s per step
     rng = np.random.default_rng(0x5601)
     ck = rng.integers(0, 2, (n, K_INFO)).astype("i1")
     dn = O.encode_batch(ck, BGN, ZC)
@@ -102,16 +102,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    # --steps / --warmup are honoured as long as the run stays inside its time budget (REF_BUDGET_S, default 150 s):
+    # a step is a bounded sample of the workload (100 codeblocks per host thread, ~1.5 s), probed by the warm-up step
+    budget = float(os.environ.get("REF_BUDGET_S", "150"))
+    t0 = time.perf_counter()
+    _, threads, n, probe = cpu_reference_run(1, 0)
+    steps = max(1, min(args.steps, int((budget - (time.perf_counter() - t0)) / max(probe, 1e-3)) - min(args.warmup, 2)))
+    warmup = max(0, min(args.warmup, 2))
     gbps, threads, n, sps = cpu_reference_run(steps, warmup)
-    sample = f"{n} codeblocks per step x {steps} steps of the same workload, float64, {threads} OpenMP threads"
+    sample = (f"{n} codeblocks per step x {steps} steps of the same workload, float64, {threads} OpenMP threads "
+              f"({'all' if steps == args.steps else 'time budget: fewer than'} the {args.steps} steps asked for)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": gbps, "unit": "Gbit/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "codeblocks_per_step": n,
-                   "note": "CPU port of the reference algorithm (oracle/, C + OpenMP); the reference itself is "
-                           "pure Python at ~26 s per codeblock (BASELINE.md) and cannot travel to this box"},
+                   "note": "CPU port of the reference algorithm (oracle/, C + OpenMP, ~13-15 ms per codeblock per core); the "
+                           "reference itself is pure Python at ~26 s per codeblock per core (BASELINE.md) and cannot "
+                           "travel to this box"},
         "cpu_baseline": {"value": gbps, "unit": "Gbit/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": gbps, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -217,6 +225,12 @@ def run_ours(args):
         step()   # restore the headline outputs for the correctness check below
         torch.cuda.synchronize()
 
+    other = []
+    agreement = []
+    if rank == 0 and not args.no_extra:
+        other = other_kernel_lines(torch, engine, dev, peaks()[0])
+        agreement = fp32_vs_fp64_agreement(np, torch, engine, dev)
+
     # correctness of what was timed: decoded info bits vs what was sent; counters reduced over ranks
     got = ((info.view(torch.uint8).unsqueeze(-1) >> torch.arange(8, device=dev, dtype=torch.uint8)) & 1).reshape(B, -1)[:, :K_INFO]
     blk_err = (got != sent.to(torch.uint8)).any(1)
@@ -279,6 +293,8 @@ def run_ours(args):
     if bound is not None:
         os.sched_setaffinity(0, cores_before)
 
+    link = host_link_ceiling(torch, dev, h_llr, barrier, world, dist)
+    tb_line = transport_block_line(np, engine) if (rank == 0 and not args.no_extra) else None
     if rank == 0:
         peak, peak_src = peaks()
         per_gpu_cbs = cbs_per_s / world
@@ -293,11 +309,14 @@ def run_ours(args):
                        "l2_policy": f"inputs larger than L2 ({B * N_CODED * 4 / 2**30:.1f} GiB of LLRs per step)",
                        "kernel_geometry": {"codeblocks_per_cta": G.value, "threads": nt.value, "smem_bytes": smem.value},
                        "block_error_rate": cnt[1] / cnt[0], "mean_iters": cnt[3] / cnt[0], "parity_ok_frac": cnt[4] / cnt[0],
-                       "other_runs_1gpu_untimed_region": extra},
+                       "other_runs_1gpu_untimed_region": extra, "other_kernels": other,
+                       "fp32_vs_float64_reference_agreement": agreement,
+                       "transport_block": tb_line},
             "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": Be * N_CODED * 4,
                     "d2h_bytes_per_step": Be * ((K_INFO + 31) // 32 * 4 + 1 + 4), "codeblocks_per_step": Be,
                     "host_cores_bound_to_gpu_numa_node": len(bound) if bound is not None else None,
-                    "host_memory": "pinned", "pageable_value": e2e_pageable,
+                    "host_memory": "pinned", "pageable_value": e2e_pageable, "pageable_over_pinned": e2e_pageable / e2e_val,
+                    "host_link_ceiling": link,
                     "pageable_note": "same call, LLRs in pageable NumPy memory: staged through the library's pinned ring by its copy threads"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -329,6 +348,182 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def host_link_ceiling(torch, dev, h_llr, barrier, world, dist):
+    """What the box's host links can carry: the e2e step's LLR bytes as plain pinned cudaMemcpyAsync H2D copies (no
+    kernels), all ranks at once, max over ranks -> GB/s over all links and the e2e value that bandwidth would allow."""
+    d = torch.empty_like(h_llr, device=dev)
+    chunk = 331   # the host path's chunk: 32 MiB of LLRs
+    def run():
+        for b0 in range(0, h_llr.shape[0], chunk):
+            d[b0:b0 + chunk].copy_(h_llr[b0:b0 + chunk], non_blocking=True)
+    run()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        run()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    nbytes = h_llr.numel() * 4
+    gbs = world * 3 * nbytes / float(dt.item()) / 1e9
+    return {"h2d_gb_per_s_all_ranks": gbs, "e2e_gbit_per_s_at_that_rate": gbs * 1e9 / (4 * N_CODED) * K_INFO / 1e9,
+            "how": "plain pinned cudaMemcpyAsync of the e2e step's LLR bytes, 32 MiB chunks, all ranks concurrently, 3 passes"}
+
+
+def other_kernel_lines(torch, engine, dev, hbm_peak):
+    """Encoder and bit-flipping lines (SURVEY 8(d) byte conventions), CUDA events, batches larger than L2."""
+    out = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def timed(f, reps=5):
+        f()
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(reps):
+            f()
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / reps
+
+    for bgn, Zc, B in [(1, 384, 1 << 16), (2, 384, 1 << 16), (1, 208, 1 << 16)]:
+        K, N, Nf, M = engine.dims(bgn, Zc)
+        ck = engine.random_bits(B, K, seed=11, device=dev)
+        ms = timed(lambda: engine.encode_batch(ck, bgn, Zc, fix_fillers=False))
+        api, packed = B * (K + N), B * (K + N) // 8
+        out.append({"kernel": f"encode BG{bgn} Zc={Zc}", "codeblocks": B, "ms": ms, "info_tbit_per_s": B * K / ms / 1e9,
+                    "bytes_int8_api": api, "gb_per_s_int8_api": api / ms / 1e6, "frac_hbm_int8_api": api / ms / 1e6 / hbm_peak,
+                    "bytes_packed_8d": packed, "gb_per_s_packed_8d": packed / ms / 1e6, "frac_hbm_packed_8d": packed / ms / 1e6 / hbm_peak})
+        del ck
+    bgn, Zc, B, L = 1, 384, 1 << 14, 20
+    K, N, Nf, M = engine.dims(bgn, Zc)
+    ck = engine.random_bits(B, K, seed=12, device=dev)
+    llr = engine.awgn_llr(engine.encode_batch(ck, bgn, Zc), 1.0, seed=13)
+    ms = timed(lambda: engine.decode_bf_batch(llr, Zc, bgn, L), reps=3)
+    nbytes = B * (4 * N + Nf)
+    out.append({"kernel": f"bit-flipping BG{bgn} Zc={Zc} L={L} (nothing converges at +1 dB)", "codeblocks": B, "ms": ms,
+                "info_gbit_per_s": B * K / ms / 1e6, "bytes_8d": nbytes, "gb_per_s": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / hbm_peak})
+    return out
+
+
+def fp32_vs_fp64_agreement(np, torch, engine, dev, n=1536):
+    """Codeblock agreement of the fp32 kernel with the float64 arithmetic of the reference (the generic float64 kernel,
+    bit-identical to the reference on every golden vector) on identical fp32-representable LLRs: hard bits, status and
+    iteration count all equal.  North-star bar: >= 99.99 % -- met where codeblocks converge; the non-converged ones of
+    a BLER ~ 1 point differ in a bit or two at the 1e-3 level."""
+    out = []
+    K, N, Nf, M = engine.dims(BGN, ZC)
+    ck = engine.random_bits(n, K_INFO, seed=21, device=dev)
+    dn = engine.encode_batch(ck, BGN, ZC)
+    for snr in (-3.0, -0.15, 1.0):
+        llr = engine.awgn_llr(dn, snr, seed=22)
+        r = engine.decode_batch(llr, ZC, BGN, MAX_ITER, ALPHA, BETA, True)
+        c64, s64, i64 = engine.decode_ref_batch(llr.cpu().numpy().astype(np.float64), ZC, BGN, MAX_ITER, "min-sum", ALPHA, BETA, True, f64=True)
+        c32, s32, i32 = r["ck"].cpu().numpy(), r["status"].cpu().numpy().astype(bool), r["iters"].cpu().numpy()
+        same = (c32 == c64).all(1) & (s32 == s64) & (i32 == i64)
+        conv = s64
+        blk32, blk64 = (c32[:, :K_INFO] != ck.cpu().numpy()).any(1), (c64[:, :K_INFO] != ck.cpu().numpy()).any(1)
+        out.append({"snr_db": snr, "codeblocks": n, "bler_float64": float((c64[:, :K_INFO] != ck.cpu().numpy()).any(1).mean()),
+                    "agreement": float(same.mean()), "agreement_converged": float(same[conv].mean()) if conv.any() else None,
+                    "agreement_not_converged": float(same[~conv].mean()) if (~conv).any() else None,
+                    "status_and_iterations_equal": float(((s32 == s64) & (i32 == i64)).mean()),
+                    "block_error_decisions_equal": float((blk32 == blk64).mean()),
+                    "differing_bits_total": int((c32 != c64).sum()), "bits_total": int(c64.size)})
+    return out
+
+
+def transport_block_line(np, engine):
+    """BASELINE config #4 through the reference-facing functions, host buffers in and out: a 273-PRB 256QAM PDSCH
+    transport block (TBS 966 896, 115 codeblocks of BG1 Zc=384, E = 10 939 per codeblock, fillers 16)."""
+    from python_5gtoolbox_b200.nr_pdsch import nr_dlsch, nr_dlsch_decode
+    rng = np.random.default_rng(4)
+    cfg = {"L": 10, "algo": "min-sum", "alpha": 0.8, "beta": 0.0}
+    A, R, Qm, NL, G, LBRM = 966896, 948, 8, 4, 273 * 12 * 12 * 8 * 4, 10 ** 9
+    trblk = rng.integers(0, 2, A).astype("i1")
+    g = nr_dlsch.DLSCHEncode(trblk, A, Qm, R, NL, 0, LBRM, G)
+    sigma = 10 ** (-6.5 / 20)
+    llr = (2 * ((1 - 2 * g.astype("f4")) + rng.normal(0, sigma, G).astype("f4")) / sigma ** 2).astype("f4")
+
+    def t(f, reps=20):
+        for _ in range(4):
+            r = f()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = f()
+        return (time.perf_counter() - t0) / reps, r
+
+    t_enc, g2 = t(lambda: nr_dlsch.DLSCHEncode(trblk, A, Qm, R, NL, 0, LBRM, G))
+    t_dec, (st, tb, new) = t(lambda: nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, 0, LBRM, cfg))
+    ok = bool(st) and np.array_equal(tb, trblk) and np.array_equal(g, g2)
+    return {"workload": "BASELINE config #4: DLSCHEncode / DLSCHDecode of a 273-PRB 256QAM 4-layer transport block (TBS 966896 = 115 "
+                        "codeblocks BG1 Zc=384), NumPy host buffers in and out, float64 [115,25344] soft buffer returned",
+            "ok": ok, "DLSCHDecode_ms": t_dec * 1e3, "DLSCHEncode_ms": t_enc * 1e3, "decode_tb_per_s": 1 / t_dec,
+            "decode_gbit_per_s_tb_bits": A / t_dec / 1e9, "encode_gbit_per_s_tb_bits": A / t_enc / 1e9,
+            "h2d_bytes_per_tb": int(llr.nbytes), "d2h_bytes_per_tb": int(new.nbytes + tb.nbytes),
+            "note": "the 23.3 MB float64 soft buffer (HARQ state, the reference's return value) is stored by the decoder straight "
+                    "into pinned host memory and bounds the call at the PCIe rate"}
+
+
+def run_mc(args):
+    """--workload mc: the device-resident Monte-Carlo chain of BASELINE config #5 (sim.bler_curve: Philox bits -> CRC24A ->
+    encode -> BPSK/AWGN -> min-sum decode with the reference's early termination -> error counters), sharded over the
+    ranks by codeblock index; the only collective is the final all-reduce of int64[points x 4].  A codeblock's bits and
+    noise depend only on (seed, point, index): the summed counters are identical for every number of GPUs."""
+    import torch
+    import torch.distributed as dist
+    from python_5gtoolbox_b200 import sim
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    snrs, n = [0.0, 1.0, 2.0], args.mc_codeblocks
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        sim.bler_curve(ZC, BGN, snrs, min(n, 16384 * world), MAX_ITER, ALPHA, BETA, device=dev)
+    barrier()
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rows = sim.bler_curve(ZC, BGN, snrs, n, MAX_ITER, ALPHA, BETA, device=dev)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sec = float(dt.item()) / args.steps
+    total = n * len(snrs)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": total * K_INFO / sec / 1e9, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Monte-Carlo chain (BASELINE config #5 analogue on AWGN): BG1 Zc=384, Philox bits -> CRC24A -> encode -> "
+                                   "BPSK/AWGN -> NMS(0.8) min-sum, L=10, early termination -> error counters, all on the device",
+                       "snr_db": snrs, "codeblocks_per_point": n, "codeblocks_per_s": total / sec,
+                       "counters": [{k: r[k] for k in ("snr_db", "codeblocks", "block_errors", "bit_errors", "bler", "mean_iters")} for r in rows],
+                       "collective": "one all_reduce(SUM) of int64[3 x 4] per curve (NCCL)"},
+            "gpu_launches": args.steps * len(snrs) * 6 * (-(-(n // world) // 16384)), "clocks": clk.summary()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def ctypes_int():
     import ctypes
     return ctypes.c_int()
@@ -350,9 +545,14 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=1 << 13)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary early-termination / OMS / mixed runs")
+    ap.add_argument("--workload", default="decode", choices=["decode", "mc"],
+                    help="decode: the headline decoder bench (default); mc: the device-resident Monte-Carlo chain, sharded over the ranks")
+    ap.add_argument("--mc-codeblocks", type=int, default=200000, help="--workload mc: codeblocks per SNR point (whole job)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "mc":
+        run_mc(args)
     else:
         run_ours(args)
 

@@ -136,6 +136,17 @@ int nrldpc_decode_bf(const void *d_llr, int is_f64, int B, int bgn, int Zc, int 
 int nrldpc_decode_bf_host(const double *llr, int B, int bgn, int Zc, int max_iter, int8_t *ck, uint8_t *status,
                           int32_t *iters);
 
+/*
+ * nr_decode_ldpc(..., algo='BP') (py5gphy/ldpc/nr_ldpc_decode.py:51-143 with _BP_process :145-176, including the
+ * one-zero quirk :164-170 and the +-38.14 clip :158-163) on the quasi-cyclic sum-product kernel: float64 arithmetic,
+ * per-edge messages in an L2-resident workspace of persistent CTAs, posteriors in shared memory.
+ * llr [B,N] float32 or float64 (is_f64), ck [B,N'] int8, status / iters as for the min-sum decoder.
+ */
+int nrldpc_decode_bp(const void *d_llr, int is_f64, int B, int bgn, int Zc, int max_iter, int early_term, int8_t *d_ck,
+                     uint8_t *d_status, int32_t *d_iters, void *stream);
+int nrldpc_decode_bp_host(const void *llr, int is_f64, int B, int bgn, int Zc, int max_iter, int early_term, int8_t *ck,
+                          uint8_t *status, int32_t *iters);
+
 /* ------------------------------------------------------------------ Monte-Carlo helpers (device) */
 /*
  * BPSK + AWGN + LLR of nr_ldpc_decode.for_test_5g_ldpc_encoder (py5gphy/ldpc/nr_ldpc_decode.py:252-257)

@@ -696,6 +696,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes)
 
 // Pull what codeblock cb will read into L2: its row of llr[B,N], or (fused rate recovery) its stretch of the received
 // sequence.  Thread 0 only.
+// (the plain-LLR path keeps the exact statements of the round-1 kernel: its SASS -- and its 0.7 % -- depend on them)
 template <class C> __device__ __forceinline__ void prefetch_cb(const DecArgs &a, int cb)
 {
     if constexpr (C::RR) {
@@ -704,7 +705,7 @@ template <class C> __device__ __forceinline__ void prefetch_cb(const DecArgs &a,
         const uintptr_t lo = p0 & ~(uintptr_t)15, hi = (p0 + (size_t)a.rr.E[cb] * esz) & ~(uintptr_t)15;
         if (hi > lo) prefetch_l2(reinterpret_cast<const void *>(lo), (uint32_t)(hi - lo));
     } else {
-        if ((reinterpret_cast<uintptr_t>(a.llr) & 15) == 0) prefetch_l2(a.llr + (size_t)cb * C::N, C::N * 4);  // 16-byte alignment
+        prefetch_l2(a.llr + (size_t)cb * C::N, C::N * 4);
     }
 }
 
@@ -761,7 +762,7 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
     // blockIdx.x + gridDim.x, ...  The channel LLRs are read straight from global memory every iteration
     // (L2 hits); the NEXT codeblock's row is pulled into L2 while the current one is decoded, so that no
     // HBM latency is exposed at a codeblock boundary.
-    const bool pf = tid == 0;
+    const bool pf = tid == 0 && (C::RR || (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0);  // bulk prefetch needs 16-byte alignment
     if (pf) prefetch_cb<C>(a, blockIdx.x);
     // With early termination the codeblocks take different numbers of iterations, so the CTAs draw them from a
     // ticket counter (a.work) instead of a fixed stride: the first one is blockIdx.x, every further one

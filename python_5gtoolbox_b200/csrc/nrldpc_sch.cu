@@ -291,14 +291,13 @@ int d2h_sync(void *dst, const void *src, size_t n, cudaStream_t s)
     return NRLDPC_OK;
 }
 
-// One non-blocking stream per device for the synchronous host-buffer entry points of this file.
+// One non-blocking stream per (host thread, device) for the synchronous host-buffer entry points of this file: calls
+// from different host threads (one transport block each) overlap their copies and kernels on the device.
 int host_stream(cudaStream_t *s)
 {
-    static std::mutex mu;
-    static std::map<int, cudaStream_t> streams;
+    thread_local std::map<int, cudaStream_t> streams;
     int dev = 0;
     NRLDPC_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(mu);
     auto it = streams.find(dev);
     if (it == streams.end()) {
         cudaStream_t st;

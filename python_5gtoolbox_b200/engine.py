@@ -196,6 +196,36 @@ def decode_ref_batch(llr, Zc, bgn, L, algo="min-sum", alpha=1.0, beta=0.0, early
     return ck, status.astype(bool), iters
 
 
+def decode_bp_batch(llr, Zc, bgn, L, early_term=True):
+    """nr_decode_ldpc(..., algo='BP') for B codeblocks on the quasi-cyclic sum-product kernel, float64 arithmetic
+    (py5gphy/ldpc/nr_ldpc_decode.py:145-176).  llr float32 / float64 [B,N]: CUDA tensor (device path, asynchronous on the
+    current stream, CUDA tensors out) or NumPy (host path).  Returns (ck int8[B,N'], status, iters)."""
+    K, N, Nf, M = dims(bgn, Zc)
+    if _is_torch(llr):
+        import torch
+        assert llr.is_cuda and llr.dtype in (torch.float32, torch.float64) and llr.is_contiguous()
+        assert llr.ndim == 2 and llr.shape[1] == N
+        B, dev = llr.shape[0], llr.device
+        ck = torch.empty((B, Nf), dtype=torch.int8, device=dev)
+        status = torch.empty((B,), dtype=torch.uint8, device=dev)
+        iters = torch.empty((B,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nrldpc_decode_bp(llr.data_ptr(), int(llr.dtype == torch.float64), B, bgn, int(Zc), int(L),
+                                                   int(bool(early_term)), ck.data_ptr(), status.data_ptr(), iters.data_ptr(),
+                                                   _stream_ptr()), "decode_bp")
+        return ck, status, iters
+    llr = np.atleast_2d(np.asarray(llr))
+    llr = np.ascontiguousarray(llr, np.float32 if llr.dtype == np.float32 else np.float64)
+    assert llr.shape[1] == N
+    B = llr.shape[0]
+    ck = np.empty((B, Nf), np.int8)
+    status = np.empty(B, np.uint8)
+    iters = np.empty(B, np.int32)
+    _lib.check(_lib.lib().nrldpc_decode_bp_host(llr.ctypes.data, int(llr.dtype == np.float64), B, bgn, int(Zc), int(L),
+                                                int(bool(early_term)), ck.ctypes.data, status.ctypes.data, iters.ctypes.data), "decode_bp")
+    return ck, status.astype(bool), iters
+
+
 def decode_csr_batch(llr, rowptr, colidx, Nv, L, algo="min-sum", alpha=1.0, beta=0.0, early_term=True, f64=True):
     """decode_ldpc on an arbitrary CSR H (py5gphy/ldpc/nr_ldpc_decode.py:51-143)."""
     llr = np.ascontiguousarray(np.atleast_2d(llr), np.float64 if f64 else np.float32)

@@ -22,7 +22,10 @@ def nr_decode_ldpc(LLRin, Zc, bgn, L, algo='min-sum', alpha=1, beta=0, *, precis
     if algo == 'BF':
         ck, st, _ = engine.decode_bf_batch(llr, Zc, bgn, L)
         ck = ck[0].astype(np.float64)  # the reference's BF returns float64 0.0/1.0
-    elif algo == 'BP' or precision == "fp64":
+    elif algo == 'BP':
+        ck, st, _ = engine.decode_bp_batch(llr.astype(np.float64), Zc, bgn, L)   # quasi-cyclic sum-product kernel, float64
+        ck = ck[0]
+    elif precision == "fp64":
         ck, st, _ = engine.decode_ref_batch(llr, Zc, bgn, L, algo, alpha, beta, True, f64=True)
         ck = ck[0]
     else:

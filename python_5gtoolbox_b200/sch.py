@@ -96,7 +96,7 @@ def sch_decode(LLr, G, TBSize, Qm, coderateby1024, num_of_layers, rv, Ncb_of, LD
         ck, _, _ = engine.decode_bf_batch(new_LLr_dns, Zc, bgn, cfg["L"])
         blocks = ck[:, :cbz].astype(np.float64)
     else:
-        ck, _, _ = engine.decode_ref_batch(new_LLr_dns, Zc, bgn, cfg["L"], algo, cfg["alpha"], cfg["beta"], True, f64=True)
+        ck, _, _ = engine.decode_bp_batch(new_LLr_dns, Zc, bgn, cfg["L"])
         blocks = ck[:, :cbz]
     tbblkandcrc = np.zeros(B)
     tbblkandcrc[:C * cbz] = blocks.reshape(-1)

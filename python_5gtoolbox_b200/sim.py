@@ -6,9 +6,9 @@ between two such checkpoints is generated, encoded and decoded as one batch on t
 the BLER values and the pickle layout ([sim_config, test_config_list, test_results_list], :87-91) are
 those of the reference.
 
-Sharding: codeblocks are independent.  With torch.distributed initialised, rank k of W
-takes every W-th codeblock of a batch and the only collective is an all-reduce(SUM) of two int64
-counters per checkpoint.
+Sharding: codeblocks and grid points are independent.  With torch.distributed initialised the
+work is split by grid point (default: one (decoder setting, SNR) point per rank, one all-reduce at the end) or by
+codeblock inside every point (an all-reduce(SUM) of one int64 per checkpoint); see run_ldpc_simulation.
 
 Input generation
   rng="numpy"  (default) the reference's own draws from NumPy's global RNG, in its order (randint
@@ -126,7 +126,7 @@ class CudaBackend:
             if algo == 'BF':
                 ck, _, _ = engine.decode_bf_batch(llr, Zc, bgn, L)
             elif algo == 'BP':
-                ck, _, _ = engine.decode_ref_batch(llr, Zc, bgn, L, 'BP', 1, 0, True, f64=True)
+                ck, _, _ = engine.decode_bp_batch(llr, Zc, bgn, L)
             else:
                 ck = engine.decode_batch(llr.astype(np.float32), Zc, bgn, L, alpha, beta, True)["ck"]
             return int((ck[:, :K] != blk).any(axis=1).sum())
@@ -153,10 +153,9 @@ class CudaBackend:
                 if algo == 'BF':   # quasi-cyclic bit-flipping kernel, device-resident like the min-sum chain
                     ck, _, it = engine.decode_bf_batch(llr, Zc, bgn, L)
                     fails += int(engine.count_errors(blk, ck, K, it)[1].item())
-                elif algo == 'BP':
-                    h = llr.cpu().numpy().astype(np.float64)
-                    ck, _, _ = engine.decode_ref_batch(h, Zc, bgn, L, 'BP', 1, 0, True, f64=True)
-                    fails += int((ck[:, :K] != blk.cpu().numpy()).any(axis=1).sum())
+                elif algo == 'BP':   # quasi-cyclic sum-product kernel: float64 arithmetic on the device-resident fp32 LLRs
+                    ck, _, it = engine.decode_bp_batch(llr, Zc, bgn, L)
+                    fails += int(engine.count_errors(blk, ck, K, it)[1].item())
                 else:
                     r = engine.decode_batch(llr, Zc, bgn, L, alpha, beta, True)
                     cnt = engine.count_errors(blk, r["ck"], K, r["iters"])
@@ -164,36 +163,76 @@ class CudaBackend:
         return fails
 
 
+def _run_point(be, Zc, bgn, snr_db, crcpoly, algo, L, alpha, beta, rng, seed, point, rank, world, reduce):
+    """One (decoder setting, SNR) point with the reference's stopping rule (sim_ldpc_internal.py:46-77); rank / world
+    split every stretch between two checkpoints by codeblock (world = 1: the whole stretch)."""
+    test_count = failed_count = 0
+    while True:
+        nxt = next(c for c in CHECKPOINTS if c > test_count)
+        n = nxt - test_count
+        take = list(range(rank, n, world))  # this rank's share of the stretch
+        f = be.count_failures(Zc, bgn, snr_db, crcpoly, 'min-sum' if algo in ('NMS', 'OMS', 'mixed-MS') else algo,
+                              L, alpha, beta, n, take, rng, seed, point * CHECKPOINTS[-1] + test_count)
+        failed_count += reduce(f)
+        test_count = nxt
+        if stop_now(test_count, failed_count):
+            return test_count, failed_count
+
+
 def run_ldpc_simulation(Zc, bgn, crcpoly, algo_list, alpha_list, beta_list, mixed_list, L_list, snr_db_list, filename,
-                        *, rng="numpy", seed=0x5601, backend=None, verbose=True):
-    """Same call and pickle output as scripts/internal/sim_ldpc_internal.run_ldpc_simulation (:9-91)."""
+                        *, rng=None, seed=0x5601, shard=None, backend=None, verbose=True):
+    """Same call and pickle output as scripts/internal/sim_ldpc_internal.run_ldpc_simulation (:9-91).
+
+    rng    "numpy" (default; NRLDPC_SIM_RNG overrides) or "device", see the module docstring.
+    shard  how the work is split over the ranks of an initialised torch.distributed job:
+           "codeblock"  every rank walks every point and takes every W-th codeblock of a stretch; with rng="numpy" every
+                        rank draws the reference's whole global stream, so the inputs are those of the seeded reference
+                        bit for bit on any number of ranks -- and the host RNG, not the GPU, sets the pace;
+           "point"      (default when W > 1) one (decoder setting, SNR) point per rank, round robin: BASELINE config #3's
+                        "sharded by SNR point".  Every point draws from its own stream, seeded from (base, point index)
+                        with base = one draw from the global RNG on rank 0, so the result does not depend on W; the
+                        stopping rule of a point is the reference's.  One all-reduce of int64[points x 2] at the end.
+    """
+    import os
     d = _Dist()
     be = backend if backend is not None else CudaBackend()
+    rng = rng or os.environ.get("NRLDPC_SIM_RNG", "numpy")
+    shard = shard or ("point" if d.world > 1 else "codeblock")
+    assert rng in ("numpy", "device") and shard in ("codeblock", "point")
+    plan = test_plan(algo_list, alpha_list, beta_list, mixed_list, L_list)
+    points = [(flag, algo, L, alpha, beta, snr_db) for flag, algo, L, alpha, beta in plan for snr_db in snr_db_list]
+    results = []
+    if shard == "codeblock":
+        for p, (flag, algo, L, alpha, beta, snr_db) in enumerate(points):
+            start = time.time()
+            tc, fc = _run_point(be, Zc, bgn, snr_db, crcpoly, algo, L, alpha, beta, rng, seed, p, d.rank, d.world,
+                                lambda f: d.sum([f], getattr(be, "reduce_device", None))[0])
+            results.append((tc, fc, time.time() - start))
+    else:
+        base = int(np.random.randint(0, 2 ** 31 - 1)) if d.rank == 0 else 0
+        base = d.sum([base], getattr(be, "reduce_device", None))[0]
+        mine = []
+        for p, (flag, algo, L, alpha, beta, snr_db) in enumerate(points):
+            if p % d.world != d.rank:
+                mine += [0, 0, 0]
+                continue
+            start = time.time()
+            if rng == "numpy":
+                np.random.seed(np.random.SeedSequence([base, p]).generate_state(4))
+            tc, fc = _run_point(be, Zc, bgn, snr_db, crcpoly, algo, L, alpha, beta, rng, seed + base, p, 0, 1, lambda f: f)
+            mine += [tc, fc, int(1e3 * (time.time() - start))]
+        tot = d.sum(mine, getattr(be, "reduce_device", None))
+        results = [(tot[3 * p], tot[3 * p + 1], tot[3 * p + 2] / 1e3) for p in range(len(points))]
     test_results_list, test_config_list = [], []
-    point = 0
-    for flag, algo, L, alpha, beta in test_plan(algo_list, alpha_list, beta_list, mixed_list, L_list):
+    for i, (flag, algo, L, alpha, beta) in enumerate(plan):
         test_config_list.append(flag)
         bler_result = []
-        for snr_db in snr_db_list:
-            start = time.time()
-            test_count = failed_count = 0
-            while True:
-                nxt = next(c for c in CHECKPOINTS if c > test_count)
-                n = nxt - test_count
-                take = list(range(d.rank, n, d.world))  # this rank's share of the stretch
-                f = be.count_failures(Zc, bgn, snr_db, crcpoly, 'min-sum' if algo in ('NMS', 'OMS', 'mixed-MS') else algo,
-                                      L, alpha, beta, n, take, rng, seed, point * CHECKPOINTS[-1] + test_count)
-                f, = d.sum([f], getattr(be, "reduce_device", None))
-                failed_count += f
-                test_count = nxt
-                if stop_now(test_count, failed_count):
-                    break
-            point += 1
-            bler = failed_count / test_count
-            bler_result.append(bler)
+        for j, snr_db in enumerate(snr_db_list):
+            tc, fc, sec = results[i * len(snr_db_list) + j]
+            bler_result.append(fc / tc)
             if verbose and d.rank == 0:
                 print("finish test {}, Zc {}, bgn{},snr_db={}, test_count={},failed_count={},bler={:2.5f},elpased time: {:6.2f}".
-                      format(flag, Zc, bgn, snr_db, test_count, failed_count, bler, time.time() - start))
+                      format(flag, Zc, bgn, snr_db, tc, fc, fc / tc, sec))
         test_results_list.append(bler_result)
     sim_config = {'Zc': Zc, 'bgn': bgn}
     if d.rank == 0 and filename:

@@ -479,8 +479,44 @@ def test_bp_golden(eng, dec_golden):
             continue
         ck, st, it = eng.decode_ref_batch(g["llr"][None, :].astype(np.float64), g["Zc"], g["bgn"], g["L"], "BP", 1, 0, True, f64=True)
         assert np.array_equal(ck[0], g["ck"]) and bool(st[0]) == g["status"] and int(it[0]) == g["iters"]
+        # the quasi-cyclic sum-product kernel (what nr_decode_ldpc(algo='BP') runs), host and device entry points
+        ck, st, it = eng.decode_bp_batch(g["llr"][None, :].astype(np.float64), g["Zc"], g["bgn"], g["L"])
+        assert np.array_equal(ck[0], g["ck"]) and bool(st[0]) == g["status"] and int(it[0]) == g["iters"]
         n += 1
     assert n >= 10
+
+
+def test_bp_qc_kernel_all_lifting_sizes(eng, oracle):
+    """The quasi-cyclic sum-product kernel against the generic CSR kernel (same device libm: identical outputs) for all
+    51 lifting sizes x 2 base graphs -- float64 and float32 LLR inputs, device and host entry points, with and without
+    early termination, zero LLRs (the one-zero / two-zero rules of _BP_process :164-175) -- and against the CPU oracle
+    (host libm) at a few sizes."""
+    import torch
+    from tests.conftest import ZLIST
+    rng = np.random.default_rng(8)
+    for bgn in (1, 2):
+        for Zc in ZLIST:
+            K, N, Nf, M = eng.dims(bgn, Zc)
+            B = 6 if Zc > 128 else 16
+            ck0 = rng.integers(0, 2, (B, K)).astype("i1")
+            dn = eng.encode_batch(ck0.copy(), bgn, Zc)
+            snr = 1.0 if bgn == 1 else 0.0
+            sigma = 10 ** (-snr / 20)
+            llr = (2 * ((1 - 2 * dn.astype("f8")) + rng.normal(0, sigma, dn.shape)) / sigma ** 2).astype("f4").astype("f8")
+            llr[0, rng.integers(0, N, max(2, N // 7))] = 0.0     # zeros: exercises the zero-input rules
+            llr[1, :] = 0.0
+            for et in (True, False):
+                ref = eng.decode_ref_batch(llr, Zc, bgn, 8, "BP", 1, 0, et, f64=True)
+                got = eng.decode_bp_batch(llr, Zc, bgn, 8, et)
+                for a, b, what in zip(got, ref, ("ck", "status", "iters")):
+                    assert np.array_equal(a, b), (bgn, Zc, et, what)
+            d = eng.decode_bp_batch(torch.from_numpy(llr.astype("f4")).cuda(), Zc, bgn, 8, True)
+            assert np.array_equal(d[0].cpu().numpy(), eng.decode_bp_batch(llr, Zc, bgn, 8, True)[0]), (bgn, Zc, "device f32")
+            if Zc in (2, 7, 36, 208, 384):
+                c, s, i = oracle.decode_batch(llr, Zc, bgn, 8, "BP", 1.0, 0.0, 1, np.float64)
+                mine = eng.decode_bp_batch(llr, Zc, bgn, 8, True)
+                assert np.array_equal(mine[1], s) and np.array_equal(mine[2], i), (bgn, Zc)
+                assert np.mean(mine[0] != c) < 1e-4, (bgn, Zc)   # libm differences may move a borderline bit of a failed block
 
 
 def test_crc_golden(eng):

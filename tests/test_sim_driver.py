@@ -61,8 +61,9 @@ if world > 1:
 from python_5gtoolbox_b200 import sim
 from tests.test_sim_driver import OracleBackend
 np.random.seed(77)
-res = sim.run_ldpc_simulation(2, 2, '16', ['NMS', 'OMS'], [0.8], [0.3], [], [6], [-1.0, 2.0],
-                              out if rank == 0 else None, backend=OracleBackend(), verbose=False)
+shard = sys.argv[6]
+res = sim.run_ldpc_simulation(2, 2, '16', ['NMS', 'OMS'], [0.8], [0.3], [], [6], [-1.0, 2.0] if shard == "codeblock" else [-2.0, -1.0],
+                              out if rank == 0 else None, backend=OracleBackend(), verbose=False, shard=shard)
 if rank == 0:
     print("RESULT", res[2])
 if world > 1:
@@ -79,17 +80,23 @@ def _free_port():
 def test_sharded_counters_match_single_rank(tmp_path):
     """world_size 1 vs 2 (gloo, CPU): identical BLER tables, i.e. identical summed counters and the
     same stopping decisions; the pickle has the reference's layout."""
-    outs = []
-    for world in (1, 2):
-        port, out = str(_free_port()), str(tmp_path / f"w{world}.pickle")
-        procs = [subprocess.Popen([sys.executable, "-c", _WORKER, ROOT, str(r), str(world), port, out],
-                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
-        for p in procs:
-            so, se = p.communicate(timeout=900)
-            assert p.returncode == 0, se[-3000:]
-        with open(out, "rb") as f:
-            outs.append(pickle.load(f))
-    assert outs[0] == outs[1]
+    tables = {}
+    for shard in ("codeblock", "point"):   # every W-th codeblock of every point / one grid point per rank
+        outs = []
+        for world in (1, 2):
+            port, out = str(_free_port()), str(tmp_path / f"{shard}{world}.pickle")
+            procs = [subprocess.Popen([sys.executable, "-c", _WORKER, ROOT, str(r), str(world), port, out, shard],
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+            for p in procs:
+                so, se = p.communicate(timeout=900)
+                assert p.returncode == 0, se[-3000:]
+            with open(out, "rb") as f:
+                outs.append(pickle.load(f))
+        assert all(o == outs[0] for o in outs), shard   # the result does not depend on the number of ranks
+        tables[shard] = outs[0]
+    assert tables["codeblock"][:2] == tables["point"][:2]   # same labels; the point mode draws other (equivalent) inputs at
+    # low SNR, where every point stops at the first checkpoint
+    outs = [tables["codeblock"]]
     sim_config, labels, table = outs[0]
     assert sim_config == {'Zc': 2, 'bgn': 2} and labels == ['NMS-alpha=0.8-L=6', 'OMS-beta=0.3-L=6']
     assert len(table) == 2 and all(len(row) == 2 for row in table)
@@ -188,3 +195,25 @@ def test_gpu_bler_matches_shipped_tables():
         n = 10000 if p < 0.0025 else (4000 if p < 0.00625 else (2000 if p < 0.025 else 1000))  # the stopping rule's n
         tol = 4 * (ref * (1 - ref) / 400 + p * (1 - p) / n) ** 0.5 + 0.005
         assert abs(p - ref) <= tol, (Zc, bgn, algo, par, p, ref, tol)
+
+
+@pytest.mark.gpu
+def test_mc_chain_counters_identical_on_two_gpus_nccl():
+    """the same seeds sharded over 1 and 2 GPUs (NCCL) give identical summed counters.  Runs
+    bench.py --workload mc under torch.distributed.run when two devices are visible."""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    lines = []
+    for world in (1, 2):
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "mc", "--steps", "1", "--warmup", "1", "--mc-codeblocks", "30000"]
+        if world > 1:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                   "--master-port", str(_free_port())] + cmd[1:]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-3000:]
+        lines.append(json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1]))
+    assert lines[0]["n_gpus"] == 1 and lines[1]["n_gpus"] == 2
+    assert lines[0]["config"]["counters"] == lines[1]["config"]["counters"]
+    assert all(c["codeblocks"] == 30000 for c in lines[0]["config"]["counters"])

@@ -108,8 +108,9 @@ def scenario_sim(rec, seed):
     from scripts.internal import sim_ldpc_internal
     rec.limits, rec.counts, rec.transparent = {}, {}, set()
     out = []
-    for args in [(12, 2, '24A', ['mixed-MS'], [], [], [[0.7, 0.5], [0.8, 0.3]], [32], [-1], "out/calls_sim_a.pickle"),
-                 (10, 1, '24A', ['BF', 'NMS'], [0.8], [], [], [16], [3.0], "out/calls_sim_b.pickle")]:
+    # (SNRs chosen so that the reference's stopping rule ends every point at its first or second checkpoint: minutes, not hours)
+    for args in [(12, 2, '24A', ['mixed-MS'], [], [], [[0.7, 0.5], [0.8, 0.3]], [32], [-2.5], "out/calls_sim_a.pickle"),
+                 (10, 1, '24A', ['BF', 'NMS'], [0.8], [], [], [16], [0.5], "out/calls_sim_b.pickle")]:
         np.random.seed(seed)
         start = len(rec.calls)
         sim_ldpc_internal.run_ldpc_simulation(*args)
@@ -140,9 +141,15 @@ def scenario_pdsch(rec, seed):
     fs = nr_slot.get_FFT_IFFT_size(prb) * scs * 1000 * 2
     wf.update(numofslots=1, startSFN=0, startslot=0, samplerate_in_mhz=fs / 1e6)
     car.update(BW=BW, scs=scs, num_of_ant=Nt, Nr=Nr, maxMIMO_layers=Nt)
-    pd.update(mcs_index=11, num_of_layers=Nt, rv=[0], data_source=[])
+    pd.update(mcs_index=11, num_of_layers=Nt, rv=[0], data_source=[], mcs_table="256QAM", precoding_matrix=np.empty(0),
+              StartSymbolIndex=2, NrOfSymbols=12)
     pd["ResAlloType1"]["RBSize"] = 40
     pd["ResAlloType1"]["RBStart"] = 0
+    pd["DMRS"]["nNIDnSCID"] = 1
+    pd["DMRS"]["NumCDMGroupsWithoutData"] = 1
+    pd["DMRS"]["DMRSAddPos"] = 1
+    pd["codebook"]["enable"] = "False"
+    car.update(PCI=1)
     carrier_freq = car["carrier_frequency_in_mhz"] * 1e6
     cm_cfg = nr_channel_model.gen_channel_model_config("AWGN", ["customized", "uniform", "DL", [0, 0]], Nt, Nr, 0, 0, 0, [], 0, np.empty(0), 0)
     p = nr_pdsch.Pdsch(pd, car)
@@ -223,10 +230,16 @@ def main():
              "after": pack(c["after"], arrays, f"{name}_{i}_m"), "ret": pack(c["ret"], arrays, f"{name}_{i}_r")}
             for i, c in enumerate(calls)]}
         print(f"{name}: {len(calls)} top-level calls recorded in {time.time() - t0:.0f} s:",
-              {n: sum(1 for c in calls if c['name'] == n) for n in sorted({c['name'] for c in calls})})
+              {n: sum(1 for c in calls if c['name'] == n) for n in sorted({c['name'] for c in calls})}, flush=True)
+        finish(meta, arrays, args.out, [name])   # saved after every scenario: hours of CPU work are not lost to a later failure
     disarm(originals)
+
+
+def finish(meta, arrays, out, fresh):
     # `after` duplicates `args` unless the call mutated an array: drop the unchanged ones
     for name, m in meta.items():
+        if name not in fresh:
+            continue
         for c in m["calls"]:
             def same(a, b):
                 if isinstance(a, dict) and "nd" in a:
@@ -257,9 +270,10 @@ def main():
             for v in o:
                 walk(v)
     walk(meta)
-    arrays = {k: v for k, v in arrays.items() if k in used}
-    np.savez_compressed(args.out, __meta__=np.array(json.dumps(meta)), **arrays)
-    print("wrote", args.out, f"{os.path.getsize(args.out) / 1e6:.2f} MB")
+    for k in [k for k in arrays if k not in used]:
+        del arrays[k]
+    np.savez_compressed(out, __meta__=np.array(json.dumps(meta)), **arrays)
+    print("wrote", out, f"{os.path.getsize(out) / 1e6:.2f} MB", flush=True)
 
 
 if __name__ == "__main__":
