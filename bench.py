@@ -290,6 +290,29 @@ def run_ours(args):
         dist.all_reduce(p_dt, op=dist.ReduceOp.MAX)
     e2e_pageable = world * Be * e_steps * K_INFO / float(p_dt.item()) / 1e9
     assert np.array_equal(p_info, h_info.numpy()), "pageable and pinned host paths disagree"
+
+    # ---- the same call with the LLRs stored as IEEE half floats in pinned host memory (nrldpc_decode_minsum_host_f16): half the
+    # bytes on the host link, widened on the device.  A different INPUT FORMAT (the LLRs are rounded to 11 significant bits
+    # before they reach the decoder), reported next to -- not instead of -- the fp32 figure.
+    h16 = torch.empty((Be, N_CODED), dtype=torch.float16).pin_memory()
+    h16.copy_(h_llr)
+    h_info16 = torch.empty_like(h_info).pin_memory()
+
+    def e2e_f16_step():
+        _lib.check(L.nrldpc_decode_minsum_host_f16(h16.data_ptr(), Be, BGN, ZC, MAX_ITER, ALPHA, BETA, 0, None,
+                                                   h_info16.data_ptr(), h_st.data_ptr(), h_it.data_ptr()), "decode_host_f16")
+
+    e2e_f16_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        e2e_f16_step()
+    barrier()
+    f_dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(f_dt, op=dist.ReduceOp.MAX)
+    e2e_f16 = world * Be * e_steps * K_INFO / float(f_dt.item()) / 1e9
+    f16_word_agreement = float((h_info16 == h_info).float().mean())
     if bound is not None:
         os.sched_setaffinity(0, cores_before)
 
@@ -317,6 +340,10 @@ def run_ours(args):
                     "host_cores_bound_to_gpu_numa_node": len(bound) if bound is not None else None,
                     "host_memory": "pinned", "pageable_value": e2e_pageable, "pageable_over_pinned": e2e_pageable / e2e_val,
                     "host_link_ceiling": link,
+                    "half_precision_llr_input": {"value": e2e_f16, "unit": "Gbit/s", "h2d_bytes_per_step": Be * N_CODED * 2,
+                                                 "info_words_equal_to_fp32_input": f16_word_agreement,
+                                                 "note": "nrldpc_decode_minsum_host_f16: the caller stores its LLRs as IEEE half floats; "
+                                                         "another input format, not the headline"},
                     "pageable_note": "same call, LLRs in pageable NumPy memory: staged through the library's pinned ring by its copy threads"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -82,6 +82,13 @@ int nrldpc_decode_minsum(const float *d_llr, int B, int bgn, int Zc, int max_ite
                          int32_t *d_iters, void *stream);
 int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
                               int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters);
+/*
+ * The same with the channel LLRs stored as IEEE half-precision floats (the format an 8- to 11-bit soft demapper fills
+ * without loss): half the bytes cross the host link -- which is what bounds the host-buffer path at R = 1/3 -- and are
+ * widened to fp32 on the device.  Arithmetic and results are those of nrldpc_decode_minsum_host on the widened values.
+ */
+int nrldpc_decode_minsum_host_f16(const uint16_t *llr_f16, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
+                                  int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters);
 
 /*
  * Mixed-(bgn, Zc) batch: group g is nrldpc_decode_minsum / nrldpc_encode on B[g] codeblocks of (bgn[g], Zc[g]) with

@@ -43,6 +43,7 @@ def _declare(L):
         "nrldpc_encode_host": (i, [p, i, i, i, i, p]),
         "nrldpc_decode_minsum": (i, [p, i, i, i, i, f, f, i, p, p, p, p, p]),
         "nrldpc_decode_minsum_host": (i, [p, i, i, i, i, f, f, i, p, p, p, p]),
+        "nrldpc_decode_minsum_host_f16": (i, [p, i, i, i, i, f, f, i, p, p, p, p]),
         "nrldpc_decode_minsum_geometry": (i, [i, i, ip, ip, ip]),
         "nrldpc_decode_minsum_groups": (i, [i, p, p, p, p, i, f, f, i, p, p, p, p, p]),
         "nrldpc_encode_groups": (i, [i, p, p, p, p, i, p, p]),

@@ -25,8 +25,12 @@ def install():
         pass
     top = types.ModuleType("matplotlib")
     plt = types.ModuleType("matplotlib.pyplot")
-    plt.__getattr__ = lambda name: _Anything()
-    top.__getattr__ = lambda name: _Anything()
+    def anything(name):
+        if name.startswith("__"):   # module protocol probes (__file__, __spec__, __wrapped__ ...) must keep failing
+            raise AttributeError(name)
+        return _Anything()
+    plt.__getattr__ = anything
+    top.__getattr__ = anything
     top.pyplot = plt
     top.__path__ = []
     sys.modules["matplotlib"] = top

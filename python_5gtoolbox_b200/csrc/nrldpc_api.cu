@@ -1,4 +1,6 @@
 // nrldpc_api.cu -- the extern "C" boundary of libnrldpc_b200.so (see include/nrldpc_b200.h).
+#include <cuda_fp16.h>
+
 #include <array>
 #include <cstdarg>
 #include <cstdio>
@@ -229,6 +231,20 @@ int fork_join(cudaStream_t caller, int ngroups, F &&launch_group)
 }  // namespace
 
 
+// IEEE half -> float, 8 values per thread (the values are exact in fp32: the decoder sees what the caller stored)
+__global__ void f16_to_f32_kernel(const uint4 *__restrict__ in, float4 *__restrict__ out, size_t n8, const __half *tail_in,
+                                  float *tail_out, int ntail)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = in[i];
+        const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+        const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+        out[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+        out[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail_out[threadIdx.x] = __half2float(tail_in[threadIdx.x]);
+}
+
 }  // namespace nrldpc
 
 using namespace nrldpc;
@@ -355,8 +371,8 @@ int nrldpc_decode_minsum_geometry(int bgn, int Zc, int *cbs_per_cta, int *thread
 // the ring.
 namespace {
 struct HostStage {
-    void *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // device: llr, ck, info, status, iters
-    size_t cap[5] = {0, 0, 0, 0, 0};
+    void *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // device: llr, ck, info, status, iters, half-precision llr
+    size_t cap[6] = {0, 0, 0, 0, 0, 0};
     void *mir[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // pinned host mirrors of the four result buffers
     size_t mcap[5] = {0, 0, 0, 0, 0};
     cudaStream_t s = nullptr;
@@ -414,10 +430,26 @@ bool host_pinned(const void *p)
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
+
 }  // namespace
+
+static int decode_minsum_host_impl(const void *llr, bool f16, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
+                                   int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters);
 
 int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
                               int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters)
+{
+    return decode_minsum_host_impl(llr, false, B, bgn, Zc, max_iter, alpha, beta, early_term, ck, info_packed, status, iters);
+}
+
+int nrldpc_decode_minsum_host_f16(const uint16_t *llr_f16, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
+                                  int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters)
+{
+    return decode_minsum_host_impl(llr_f16, true, B, bgn, Zc, max_iter, alpha, beta, early_term, ck, info_packed, status, iters);
+}
+
+static int decode_minsum_host_impl(const void *llr, bool f16, int B, int bgn, int Zc, int max_iter, float alpha, float beta,
+                                   int early_term, int8_t *ck, uint32_t *info_packed, uint8_t *status, int32_t *iters)
 {
     const QcCfg *c = get_cfg(bgn, Zc);
     if (!c) return NRLDPC_EINVAL;
@@ -444,6 +476,7 @@ int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_
     for (int i = 0; i < nstage && rc == NRLDPC_OK; ++i) {
         if (!st[i].s && cudaStreamCreateWithFlags(&st[i].s, cudaStreamNonBlocking) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamCreate");
         if (rc == NRLDPC_OK) rc = st[i].ensure(0, (size_t)chunk * llr_bytes);
+        if (rc == NRLDPC_OK && f16) rc = st[i].ensure(5, (size_t)chunk * llr_bytes / 2);
         for (int w = 1; w < 5 && rc == NRLDPC_OK; ++w) {
             if (w <= 2 && !res[w].p) continue;  // ck / info are optional kernel outputs; status and iters are always produced
             rc = st[i].ensure(w, (size_t)chunk * res[w].per);
@@ -456,7 +489,17 @@ int nrldpc_decode_minsum_host(const float *llr, int B, int bgn, int Zc, int max_
         HostStage &S = st[k % nstage];
         const int nb = std::min(chunk, B - b0);
         if ((rc = S.drain()) != NRLDPC_OK) return fail(rc);
-        if ((rc = h2d_async(S.buf[0], llr + (size_t)b0 * c->N, (size_t)nb * llr_bytes, S.s)) != NRLDPC_OK) return fail(rc);
+        if (!f16) {
+            if ((rc = h2d_async(S.buf[0], (const float *)llr + (size_t)b0 * c->N, (size_t)nb * llr_bytes, S.s)) != NRLDPC_OK) return fail(rc);
+        } else {  // half the bytes over the host link, widened on the device (one HBM pass, ~1 % of the decode time)
+            const size_t n = (size_t)nb * c->N;
+            if ((rc = h2d_async(S.buf[5], (const uint16_t *)llr + (size_t)b0 * c->N, n * 2, S.s)) != NRLDPC_OK) return fail(rc);
+            const size_t n8 = n / 8;
+            const int grid = (int)std::min<size_t>(148 * 8, std::max<size_t>(1, (n8 + 255) / 256));
+            f16_to_f32_kernel<<<grid, 256, 0, S.s>>>((const uint4 *)S.buf[5], (float4 *)S.buf[0], n8, (const __half *)S.buf[5] + n8 * 8,
+                                                    (float *)S.buf[0] + n8 * 8, (int)(n - n8 * 8));
+            if (cudaGetLastError() != cudaSuccess) return fail(cuda_fail(cudaPeekAtLastError(), "f16_to_f32_kernel"));
+        }
         if ((rc = launch_decode_minsum(*c, (const float *)S.buf[0], nb, max_iter, alpha, beta, early_term,
                                        ck ? (int8_t *)S.buf[1] : nullptr, info_packed ? (uint32_t *)S.buf[2] : nullptr,
                                        (uint8_t *)S.buf[3], (int32_t *)S.buf[4], S.s)) != NRLDPC_OK)

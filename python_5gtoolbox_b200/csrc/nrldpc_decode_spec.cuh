@@ -38,6 +38,11 @@ namespace nrldpc {
 namespace {
 
 constexpr int kMaxS = 16;  // warp groups per r-tile
+#ifndef NRLDPC_MULTI_CTA_BELOW
+#define NRLDPC_MULTI_CTA_BELOW 176
+#endif
+constexpr int kMultiCtaBelow = NRLDPC_MULTI_CTA_BELOW;  // lifting sizes below this run several persistent CTAs per SM
+constexpr int kNoVariant = 1;  // launch_spec: this (early_term) combination is not instantiated -> table-driven kernel
 #ifndef NRLDPC_COLD_FMA
 #define NRLDPC_COLD_FMA 1
 #endif
@@ -119,7 +124,7 @@ template <int BGN, int ZC_, bool RR_ = false> struct Code {
     static constexpr bool RR = RR_;
     // Any lifting size >= 64: r-tile 0 must be full (it writes the 32 mirrored elements).  In a partial last
     // tile the lanes beyond Zc duplicate lane Zc-1 (same loads, same stores of the same values).
-    static_assert(iLS >= 0 && ZC_ >= 64, "specialised kernels need a lifting size >= 64");
+    static_assert(iLS >= 0 && ZC_ >= 32, "specialised kernels need a lifting size >= 32 (a full first r-tile)");
     static constexpr int nrows = G::rows, kb = G::kb, ncore = G::kb + 4, nnz = G::nnz;
     static constexpr int K = kb * ZC, N = (G::cols - 2) * ZC, Nfull = G::cols * ZC;
     static constexpr int tiles = (ZC + 31) / 32;
@@ -157,8 +162,15 @@ template <int BGN, int ZC_, bool RR_ = false> struct Code {
     static constexpr int smem_bytes = (off_ext + (nrows - 4) * tiles * 4 + 15) & ~15;
     // CTAs per SM: two when two codeblock states (+ 1 KB of system shared memory each) fit in the SM's 228 KB; each then
     // runs 16 / tiles warp groups (at most 512 threads, so that two CTAs keep >= 64 registers per thread)
-    static constexpr int ctas = (NRLDPC_TWO_CTAS && 2 * (smem_bytes + 1024) <= 228 * 1024 && 16 / tiles >= 1) ? 2 : 1;
-    static constexpr int Smax = (ctas == 2 ? 16 : 32) / tiles;
+    // Small lifting sizes (ZC < 144): one codeblock no longer fills an SM, so as many persistent CTAs as fit in its shared
+    // memory run side by side (each its own codeblock, its own barriers: the check pass of one overlaps the variable pass of
+    // another), with the SM's 32 warps shared between them.
+    static constexpr int fit = (228 * 1024) / (smem_bytes + 1024);
+    static constexpr int ctas_small = fit > 8 ? 8 : (fit < 1 ? 1 : fit);
+    static constexpr int ctas = ZC < kMultiCtaBelow ? ctas_small
+                                         : ((NRLDPC_TWO_CTAS && 2 * (smem_bytes + 1024) <= 228 * 1024 && 16 / tiles >= 1) ? 2 : 1);
+    static constexpr int Smax0 = (32 / ctas) / tiles;
+    static constexpr int Smax = Smax0 < 1 ? 1 : Smax0;
     static constexpr int S = Smax < kMaxS ? Smax : kMaxS, nwarps = tiles * S;
     static constexpr int lq_base(int j) { return off_lq + j * LQS * 4; }
     static constexpr int mags_base(int i) { return off_mags + i * LQS * 4; }  // mag1 of check 0; mag2 sits mag2_dist further
@@ -930,13 +942,23 @@ int launch_spec(const DecArgs &a, int early_term, cudaStream_t s)
         NRLDPC_CUDA(cudaGetLastError());
         return NRLDPC_OK;
     };
+    // the lifting sizes below 144 are instantiated for the reference's semantics only (early termination; beta = 0 and
+    // beta as a run-time value, plus the fused rate recovery): fixed-iteration runs go to the table-driven kernel there.
+    // This keeps the library's build time and size in check (6 kernels of ~170 KB of SASS per (bgn, Zc) otherwise).
+    constexpr bool lean = C::ZC < 144;
     if (a.rr.src) {
         using CR = Code<C::bgn, C::ZC, true>;
         if (!early_term) { set_error("decode: the fused rate recovery runs with early termination only"); return NRLDPC_EINVAL; }
-        return a.beta == 0.f ? launch(decode_spec_kernel<CR, true, true>) : launch(decode_spec_kernel<CR, true, false>);
+        if constexpr (!lean) if (a.beta == 0.f) return launch(decode_spec_kernel<CR, true, true>);
+        return launch(decode_spec_kernel<CR, true, false>);
     }
-    if (a.beta == 0.f) return early_term ? launch(decode_spec_kernel<C, true, true>) : launch(decode_spec_kernel<C, false, true>);
-    return early_term ? launch(decode_spec_kernel<C, true, false>) : launch(decode_spec_kernel<C, false, false>);
+    if constexpr (lean) {
+        if (!early_term) return kNoVariant;
+        return a.beta == 0.f ? launch(decode_spec_kernel<C, true, true>) : launch(decode_spec_kernel<C, true, false>);
+    } else {
+        if (a.beta == 0.f) return early_term ? launch(decode_spec_kernel<C, true, true>) : launch(decode_spec_kernel<C, false, true>);
+        return early_term ? launch(decode_spec_kernel<C, true, false>) : launch(decode_spec_kernel<C, false, false>);
+    }
 }
 
 }  // namespace

@@ -112,12 +112,13 @@ def decode_batch(llr, Zc, bgn, L, alpha=1.0, beta=0.0, early_term=True, want_ck=
                                                info.data_ptr() if want_info else None, status.data_ptr(),
                                                iters.data_ptr(), _stream_ptr()), "decode_minsum")
         return dict(ck=ck, info=info, status=status, iters=iters)
-    llr = np.ascontiguousarray(llr, np.float32)
+    f16 = llr.dtype == np.float16   # half-precision LLRs cross the host link as they are and are widened on the device
+    llr = np.ascontiguousarray(llr, np.float16 if f16 else np.float32)
     ck = np.empty((B, Nf), np.int8) if want_ck else None
     info = np.empty((B, nw), np.uint32) if want_info else None
     status = np.empty(B, np.uint8)
     iters = np.empty(B, np.int32)
-    _lib.check(Lb.nrldpc_decode_minsum_host(llr.ctypes.data, B, bgn, int(Zc), int(L), float(alpha), float(beta),
+    _lib.check((Lb.nrldpc_decode_minsum_host_f16 if f16 else Lb.nrldpc_decode_minsum_host)(llr.ctypes.data, B, bgn, int(Zc), int(L), float(alpha), float(beta),
                                             int(bool(early_term)), ck.ctypes.data if want_ck else None,
                                             info.ctypes.data if want_info else None, status.ctypes.data,
                                             iters.ctypes.data), "decode_minsum")

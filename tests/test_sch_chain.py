@@ -400,3 +400,19 @@ def test_early_termination_queue_under_graph_capture(eng):
         for k in ("ck", "status", "iters"):
             assert torch.equal(out[k], ref[k]), (rep, k)
             assert torch.equal(eager[k], ref[k]), (rep, k)
+
+
+@pytest.mark.gpu
+def test_half_precision_host_llrs(eng):
+    """nrldpc_decode_minsum_host_f16: half-precision LLRs over the host link, widened on the device -- the results are those of
+    the fp32 entry point on the widened values, for batches with a tail that is not a multiple of 8 values."""
+    import torch
+    for bgn, Zc, B in [(1, 384, 350), (2, 7, 33)]:
+        K, N, Nf, M = eng.dims(bgn, Zc)
+        ck = eng.random_bits(B, K, seed=15, device="cuda")
+        llr = eng.awgn_llr(eng.encode_batch(ck, bgn, Zc), 1.5, seed=16).cpu().numpy()
+        h = llr.astype(np.float16)
+        want = eng.decode_batch(h.astype(np.float32), Zc, bgn, 10, 0.8, 0.0, True, want_info=True)
+        got = eng.decode_batch(h, Zc, bgn, 10, 0.8, 0.0, True, want_info=True)
+        for k in ("ck", "info", "status", "iters"):
+            assert np.array_equal(got[k], want[k]), (bgn, Zc, k)
