@@ -348,6 +348,8 @@ def run_ours(args):
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": TRAFFIC_BYTES_PER_CB * B, "peak_source": peak_src,
+                         "traffic_source": f"{NCU_CAPTURE}: (dram__bytes_read.sum + dram__bytes_write.sum) / 592 codeblocks x this "
+                                           "launch's codeblocks (cited from the committed capture, not measured by this run)",
                          "algorithmic_bytes_per_launch": B * ALGO_BYTES_PER_CB,
                          "kernel": "decode_spec_kernel<Code<1,384>,ET=0,B0=1>", "kernel_ms": ms / args.steps,
                          "note": "HBM is not the binding roof of this kernel (10 on-chip iterations per byte): the check "
@@ -362,8 +364,8 @@ def run_ours(args):
         out["roofline_onchip"] = {"bound": "issue_slots", "achieved": per_gpu_cbs * WARP_INSTR_PER_CB / 1e9,
                                   "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": per_gpu_cbs * WARP_INSTR_PER_CB / issue_peak,
                                   "warp_instr_per_codeblock": WARP_INSTR_PER_CB,
-                                  "source": "smsp__inst_executed.sum of profiles/prof_r1i.ncu-rep / 592 codeblocks; ALU pipe 68 %, "
-                                            "issue 78 %, smem wavefronts 62 % busy in that capture"}
+                                  "source": f"smsp__inst_executed.sum of {NCU_CAPTURE} / 592 codeblocks (cited, not measured by this run); "
+                                            "ALU pipe 68 %, issue 78 %, smem wavefronts 62 % busy in that capture"}
         if not args.no_cpu and world == 1:   # reported at N=1 only (rank 0); ~10 s of CPU work on all host cores
             ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             gbps, threads, n, sps = cpu_reference_run(1, 0, sample_cbs=max(400 * ncores, 256))
@@ -556,10 +558,12 @@ def ctypes_int():
     return ctypes.c_int()
 
 
-# From the committed `ncu --set full` capture (profiles/r1_decode_spec_ncu_summary.md, 592 codeblocks):
-# dram__bytes_read.sum + dram__bytes_write.sum = 60.151 MB + 0.292 MB; smsp__inst_executed.sum = 495.07 M
-TRAFFIC_BYTES_PER_CB = (60151296 + 291840) / 592
-WARP_INSTR_PER_CB = 466162704 / 592
+# Cited, not measured by this run: the committed `ncu --set full` capture of the same kernel, profiles/prof_r2_decode.ncu-rep
+# (592 codeblocks; raw page profiles/prof_r2_decode_raw.csv, summary profiles/r2_ncu_summary.md):
+#   dram__bytes_read.sum + dram__bytes_write.sum = 60 183 808 B + 389 376 B;  smsp__inst_executed.sum = 466 189 936
+NCU_CAPTURE = "profiles/prof_r2_decode.ncu-rep"
+TRAFFIC_BYTES_PER_CB = (60183808 + 389376) / 592
+WARP_INSTR_PER_CB = 466189936 / 592
 
 
 def main():

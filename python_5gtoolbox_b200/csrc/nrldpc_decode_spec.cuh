@@ -39,7 +39,7 @@ namespace {
 
 constexpr int kMaxS = 16;  // warp groups per r-tile
 #ifndef NRLDPC_MULTI_CTA_BELOW
-#define NRLDPC_MULTI_CTA_BELOW 176
+#define NRLDPC_MULTI_CTA_BELOW 144  // (176 measured: BG1 Zc=160 785 vs 826, Zc=144 712 vs 745 G edge-iterations/s -- one CTA of 30 warps wins there)
 #endif
 constexpr int kMultiCtaBelow = NRLDPC_MULTI_CTA_BELOW;  // lifting sizes below this run several persistent CTAs per SM
 constexpr int kNoVariant = 1;  // launch_spec: this (early_term) combination is not instantiated -> table-driven kernel
