@@ -92,7 +92,16 @@ struct ScratchBuf {
 };
 
 // kernel launchers (device pointers)
-int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s);
+// Rate matching fused into the encoder's store (nrldpc_encode.cu): g != nullptr -> the encoder writes the rate-matched,
+// concatenated sequence g (codeblock b: E[b] bytes at g + goff[b]) instead of dn; fillers = the dn positions [F0, F1).
+struct EncRmArgs {
+    int8_t *g = nullptr;
+    const int32_t *E = nullptr;
+    const long long *goff = nullptr;
+    int Ncb = 0, k0 = 0, Qm = 1, F0 = 0, F1 = 0;
+};
+int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s,
+                  const EncRmArgs *rm = nullptr);
 struct RrArgs;  // nrldpc_raterecover.cuh
 // rr != nullptr: the LLR load is the rate recovery of a transport block (d_llr unused, early_term must be 1)
 int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_iter, float alpha, float beta,

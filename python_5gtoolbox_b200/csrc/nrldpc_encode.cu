@@ -16,6 +16,38 @@ namespace {
 
 constexpr int kEncThreads = 256;
 
+// Rate matching fused into the encoder's store ("bit-select + Qm interleave into the encoder's store"):
+// nr_ldpc_ratematch.ratematch_ldpc (py5gphy/ldpc/nr_ldpc_ratematch.py:64-97) + code block concatenation
+// (py5gphy/nr_pdsch/nr_dlsch.py:66-68) in gather form, straight from the packed codeword in shared memory -- dn never
+// exists.  Output byte o of codeblock cb is bit k = (o mod Qm) * E/Qm + o div Qm of the selection (:90-93), i.e. the
+// (k mod S)-th non-filler position of the walk that starts at k0 on the circular buffer of length Ncb (:80-87; S = the
+// number of non-filler positions, the fillers are the buffer positions [F0, F1)).
+template <class BitAt>
+__device__ __forceinline__ void rm_store(const EncRmArgs &rm, int cb, BitAt bit_at, int tid, int nthreads)
+{
+    const int E = rm.E[cb], Qm = rm.Qm, Ncb = rm.Ncb, k0 = rm.k0;
+    int8_t *out = rm.g + rm.goff[cb];
+    const int f0 = min(max(rm.F0, 0), Ncb), f1 = min(max(rm.F1, f0), Ncb), nf = f1 - f0, S = Ncb - nf;
+    if (S <= 0 || E <= 0) return;
+    // rank r of a non-filler position -> its step t of the walk: the fillers form one stretch [a, a + nf) of the walk, or
+    // (k0 inside the fillers) its first `lead` steps and its tail
+    int a, skip, lead = 0;
+    if (k0 <= f0) { a = f0 - k0; skip = nf; }
+    else if (k0 >= f1) { a = f0 - k0 + Ncb; skip = nf; }
+    else { a = Ncb; skip = 0; lead = f1 - k0; }
+    const int cols = E / Qm;
+    for (int o = tid; o < E; o += nthreads) {
+        const int e = o / Qm, q = o - e * Qm;
+        int r = q * cols + e;
+        if (r >= S) r -= (r / S) * S;  // repetition when E exceeds the buffer
+        int t = r + lead;
+        if (t >= a) t += skip;
+        int pos = k0 + t;
+        if (pos >= Ncb) pos -= Ncb;
+        out[o] = (int8_t)bit_at(pos);
+    }
+}
+
 __device__ __forceinline__ int find_edge(const QcCfg &c, int i, int j)
 {
     for (int e = c.rowptr[i]; e < c.rowptr[i + 1]; ++e)
@@ -25,7 +57,7 @@ __device__ __forceinline__ int find_edge(const QcCfg &c, int i, int j)
 
 __global__ void __launch_bounds__(kEncThreads)
 encode_kernel(const __grid_constant__ QcCfg c, int8_t *__restrict__ ck, int B, int G, int fix_fillers,
-              int8_t *__restrict__ dn, int vec)
+              int8_t *__restrict__ dn, int vec, const __grid_constant__ EncRmArgs rm)
 {
     extern __shared__ uint32_t smem[];
     const int Zc = c.Zc, W = c.tiles, Wp = W + 1;
@@ -137,6 +169,16 @@ encode_kernel(const __grid_constant__ QcCfg c, int8_t *__restrict__ ck, int B, i
     }
     __syncthreads();
 
+    // D'. rate matching fused into the store: g straight from the packed codeword
+    if (rm.g) {
+        const uint32_t mZ = 0xffffffffu / (uint32_t)Zc + 1u;  // pos / Zc by multiplication: exact for pos * Zc < 2^32
+        for (int g = 0; g < g_cnt; ++g)
+            rm_store(rm, cb0 + g, [&](int pos) {
+                const int jo = (int)__umulhi((uint32_t)pos, mZ), r = pos - jo * Zc;
+                return (V(g, jo + 2)[r >> 5] >> (r & 31)) & 1u;
+            }, threadIdx.x, kEncThreads);
+        return;
+    }
     // D. unpack dn = codeword without the first 2Zc bits; -1 at filler positions (:31-37,:47-48)
     const int nout = c.ncols - 2;
     if (vec) {
@@ -222,6 +264,7 @@ struct EncWordArgs {
     uint16_t nsys[kWParts], next[kWParts];
     uint32_t sys[kWParts][kWSysMax];   // systematic edges of row-block `part`
     uint32_t ext[kWParts][kWExtMax];   // edges (all but the last) of row-blocks 4 + part, 8 + part, ...
+    EncRmArgs rm;                      // rm.g != nullptr: rate matching fused into the store, dn is not written
 };
 
 __device__ __forceinline__ uint32_t rot2d(const uint32_t *v2w, uint32_t d)
@@ -335,6 +378,15 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
     }
     __syncthreads();
 
+    // D'. rate matching fused into the store: OUT holds dn's N bits of every codeblock contiguously (Zc = 32 W), so
+    // dn[pos] is bit pos of the codeblock's OUT words
+    if (a.rm.g) {
+        for (int gg = 0; gg < g_cnt; ++gg) {
+            const uint32_t *words = OUT + gg * nout * W;
+            rm_store(a.rm, cb0 + gg, [&](int pos) { return (words[pos >> 5] >> (pos & 31)) & 1u; }, threadIdx.x, kWThreads);
+        }
+        return;
+    }
     // D. unpack dn: one thread per 16 output bytes, contiguous in dn and in OUT for the CTA's codeblocks
     {
         const int total = g_cnt * NH, FH = (kb - 2) * H;
@@ -367,11 +419,12 @@ int find_edge_host(const QcCfg &c, int i, int j)
     return 0;
 }
 
-int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s)
+int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s, const EncRmArgs &rm)
 {
     const int W = c.tiles, H = 2 * W, kb = c.kb, nout = c.ncols - 2, Zc = c.Zc;
     EncWordArgs a = {};
     a.bgn = c.bgn; a.W = W; a.kb = kb; a.nout = nout; a.K = c.K; a.N = c.N;
+    a.rm = rm;
     a.G = kWPart / W;
     int slot = (kb + 8) * 2 * W + (kb - 2) * W;
     slot += ((W - slot) % 32 + 32) % 32;  // slot = W (mod 32): thread (g, w) falls in bank (g W + w) mod 32
@@ -425,11 +478,13 @@ int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, in
 
 }  // namespace
 
-int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s)
+int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s, const EncRmArgs *rm_in)
 {
     if (B <= 0) return NRLDPC_OK;
+    EncRmArgs rm;
+    if (rm_in) rm = *rm_in;
     if (cfg.Zc % 32 == 0 && (reinterpret_cast<uintptr_t>(d_ck) | reinterpret_cast<uintptr_t>(d_dn)) % 16 == 0)
-        return launch_encode_words(cfg, d_ck, B, fix_fillers, d_dn, s);
+        return launch_encode_words(cfg, d_ck, B, fix_fillers, d_dn, s, rm);
     const int Wp = cfg.tiles + 1;
     const int slot_bytes = (cfg.ncols * Wp + cfg.kb * cfg.tiles + 5 * Wp) * 4;
     // enough codeblocks per CTA to give 256 threads work, bounded by 48 KB of static-limit shared memory
@@ -437,7 +492,7 @@ int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t
     while (G < 16 && (G * 2) * slot_bytes <= 48 * 1024 && G * cfg.nrows * cfg.tiles < 2 * kEncThreads) G *= 2;
     const int grid = (B + G - 1) / G;
     const int vec = (cfg.Zc % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_ck) | reinterpret_cast<uintptr_t>(d_dn)) % 16 == 0);
-    encode_kernel<<<grid, kEncThreads, G * slot_bytes, s>>>(cfg, d_ck, B, G, fix_fillers, d_dn, vec);
+    encode_kernel<<<grid, kEncThreads, G * slot_bytes, s>>>(cfg, d_ck, B, G, fix_fillers, d_dn, vec, rm);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
 }

@@ -842,9 +842,20 @@ int encode_chain_host(const int8_t *trblk, int A, int8_t *cbs, int C, int bgn, i
     } else {
         rc = h2d_async(d_cbs.p, cbs, (size_t)C * c->K, s);
     }
-    if (rc == NRLDPC_OK)
+    if (rc == NRLDPC_OK && trblk) {
+        // the codeblocks come from tb_segment_kernel: the fillers are the tail [K_apo, K) of every row, so the rate matching
+        // runs inside the encoder's store and dn never exists
+        const int Lcb = C > 1 ? 24 : 0, Ltb = A > 3824 ? 24 : 16;
+        EncRmArgs rm;
+        rm.g = d_g.as<int8_t>(); rm.E = d_E.as<int32_t>(); rm.goff = d_off.as<long long>();
+        rm.Ncb = Ncb; rm.k0 = k0; rm.Qm = Qm;
+        rm.F0 = (A + Ltb) / C + Lcb - 2 * Zc; rm.F1 = c->K - 2 * Zc;
+        if (Ncb <= 0 || Ncb > c->N || k0 < 0 || k0 >= Ncb || Qm <= 0) { set_error("sch_encode: bad rate-matching arguments"); rc = NRLDPC_EINVAL; }
+        else rc = launch_encode(*c, d_cbs.as<int8_t>(), C, 1, d_g.as<int8_t>() /* unused */, s, &rm);
+    } else if (rc == NRLDPC_OK) {  // caller-provided codeblocks may carry any -1 pattern: encoder, then the scanning rate matcher
         rc = nrldpc_encode_ratematch(d_cbs.as<int8_t>(), C, bgn, Zc, fix_fillers, Ncb, k0, Qm, d_E.as<int32_t>(), d_off.as<long long>(),
                                      d_g.as<int8_t>(), s);
+    }
     if (rc == NRLDPC_OK && !trblk && fix_fillers) {  // the reference's in-place side effect on the caller's cbs (nr_ldpc_encode.py:32-35)
         cudaError_t e = cudaMemcpyAsync(cbs, d_cbs.p, (size_t)C * c->K, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync(cbs)");
