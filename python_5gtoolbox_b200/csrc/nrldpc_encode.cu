@@ -256,7 +256,7 @@ constexpr int kWSysMax = 20, kWExtMax = 72;
 //   (byte offset of word j*2W + (P >> 5) inside the codeblock's doubled column array) << 16 | last-of-row << 5 | (P & 31)
 // so that the address is one LEA.HI and the descriptor itself is the funnel-shift amount (the shift wraps mod 32).
 struct EncWordArgs {
-    int bgn, W, kb, nout, K, N;
+    int bgn, W, H, kb, nout, K, N;   // W = ceil(Zc/32) words (threads) per column-block, H = Zc/16 half words
     int G, slot;                 // codeblocks per CTA, words of shared memory per codeblock (without dn's words)
     uint32_t mKH, mNH, mH;       // floor(2^32 / d) + 1 for d = kb*H, nout*H, H   (H = Zc/16)
     int s1, s2, s3, s4;          // composed rotations of the closed-form core parity
@@ -279,14 +279,31 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
 {
     extern __shared__ uint32_t smem[];
     __shared__ int any_filler;
-    const int W = a.W, W2 = 2 * W, H = 2 * W, kb = a.kb, nout = a.nout;
+    // A column-block is H = Zc/16 half words.  Stored twice back to back it is a bit-contiguous array of 2 Zc bits = H
+    // words (W2), whatever the parity of H: for Zc = 16 * odd the second copy simply starts on a half-word boundary, which
+    // is why every store into a doubled array below is made of half words.  W = ceil(H/2) threads cover a column-block;
+    // in the last word of an odd H only the low half is valid.
+    const int W = a.W, H = a.H, W2 = H, kb = a.kb, nout = a.nout;
+    const bool odd = H & 1;
     const int cb0 = blockIdx.x * a.G, g_cnt = min(a.G, B - cb0);
-    // per codeblock slot: D2[kb+4][2W] (systematic + core parity, doubled), L2x[4][2W] (L1 rows, doubled),
-    // FM[kb-2][W] (filler masks, indexed like dn's words); then OUT[G][nout][W]: dn as words, contiguous over the
-    // CTA's codeblocks like dn itself
+    // per codeblock slot: D2[kb+4][H words] (systematic + core parity, doubled), L2x[4][H words] (L1 rows, doubled),
+    // FM[kb-2][H half words] (filler masks, indexed like dn's half words); then OUT[G][nout][H half words]: dn packed,
+    // contiguous over the CTA's codeblocks like dn itself
     const int oL1 = (kb + 4) * W2, oFM = oL1 + 4 * W2;
     uint32_t *OUT = smem + a.G * a.slot;
     const int NH = nout * H;
+    // word `v` of thread (g, w) into a doubled array (both copies) / into dn's packed half words
+    auto store2 = [&](uint32_t *arr, int w, uint32_t v) {
+        if (!odd) { arr[w] = v; arr[W + w] = v; return; }
+        uint16_t *h = reinterpret_cast<uint16_t *>(arr);
+        h[2 * w] = (uint16_t)v; h[H + 2 * w] = (uint16_t)v;
+        if (2 * w + 1 < H) { h[2 * w + 1] = (uint16_t)(v >> 16); h[H + 2 * w + 1] = (uint16_t)(v >> 16); }
+    };
+    auto store_out = [&](uint16_t *o16, int w, uint32_t v) {  // o16 = the column-block's first half word inside OUT
+        if (!odd) { reinterpret_cast<uint32_t *>(o16)[w] = v; return; }
+        o16[2 * w] = (uint16_t)v;
+        if (2 * w + 1 < H) o16[2 * w + 1] = (uint16_t)(v >> 16);
+    };
     if (threadIdx.x == 0) any_filler = 0;
     __syncthreads();
 
@@ -329,7 +346,7 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
     const int g = x / W, w = x - g * W;
     const bool act = g < g_cnt;
     uint32_t *cb = smem + g * a.slot;
-    uint32_t *out = OUT + g * nout * W + w;
+    uint16_t *out16 = reinterpret_cast<uint16_t *>(OUT) + g * NH;  // dn's half words of codeblock g
     const uint32_t *Dw = cb + w;
 
     // B. L1[part] = sum over the systematic edges of row-block `part` (:92)
@@ -337,8 +354,7 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
         uint32_t acc = 0;
         const int n = a.nsys[part];
         for (int e = 0; e < n; ++e) acc ^= rot2d(Dw, a.sys[part][e]);
-        cb[oL1 + part * W2 + w] = acc;
-        cb[oL1 + part * W2 + W + w] = acc;
+        store2(cb + oL1 + part * W2, w, acc);
     }
     __syncthreads();
 
@@ -354,9 +370,8 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
             if (a.bgn == 1) acc ^= Lw[2 * W2] ^ rot2(Lw + 3 * W2, a.p3);
             else acc ^= Lw[W2] ^ rot2(Lw, a.p3);
         }
-        cb[(kb + part) * W2 + w] = acc;
-        cb[(kb + part) * W2 + W + w] = acc;
-        out[(kb - 2 + part) * W] = acc;
+        store2(cb + (kb + part) * W2, w, acc);
+        store_out(out16 + (kb - 2 + part) * H, w, acc);
     }
     __syncthreads();
 
@@ -364,15 +379,15 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
     // edge list per part, the descriptor's bit 5 closes a row-block
     if (act) {
         uint32_t acc = 0;
-        uint32_t *o = out + (kb + 2 + part) * W;  // row-block 4 + part -> dn column-block kb - 2 + 4 + part
+        uint16_t *o = out16 + (kb + 2 + part) * H;  // row-block 4 + part -> dn column-block kb - 2 + 4 + part
         const int n = a.next[part];
         for (int e = 0; e < n; ++e) {
             const uint32_t d = a.ext[part][e];
             acc ^= rot2d(Dw, d);
             if (d & 32u) {
-                *o = acc;
+                store_out(o, w, acc);
                 acc = 0;
-                o += kWParts * W;
+                o += kWParts * H;
             }
         }
     }
@@ -382,7 +397,7 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
     // dn[pos] is bit pos of the codeblock's OUT words
     if (a.rm.g) {
         for (int gg = 0; gg < g_cnt; ++gg) {
-            const uint32_t *words = OUT + gg * nout * W;
+            const uint32_t *words = OUT + gg * (NH / 2);  // NH = nout * H is even (nout = 66 | 50)
             rm_store(a.rm, cb0 + gg, [&](int pos) { return (words[pos >> 5] >> (pos & 31)) & 1u; }, threadIdx.x, kWThreads);
         }
         return;
@@ -421,12 +436,13 @@ int find_edge_host(const QcCfg &c, int i, int j)
 
 int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s, const EncRmArgs &rm)
 {
-    const int W = c.tiles, H = 2 * W, kb = c.kb, nout = c.ncols - 2, Zc = c.Zc;
+    const int Zc = c.Zc, H = Zc / 16, W = (H + 1) / 2, kb = c.kb, nout = c.ncols - 2;
     EncWordArgs a = {};
-    a.bgn = c.bgn; a.W = W; a.kb = kb; a.nout = nout; a.K = c.K; a.N = c.N;
+    a.bgn = c.bgn; a.W = W; a.H = H; a.kb = kb; a.nout = nout; a.K = c.K; a.N = c.N;
     a.rm = rm;
     a.G = kWPart / W;
-    int slot = (kb + 8) * 2 * W + (kb - 2) * W;
+    int slot = (kb + 8) * H + ((kb - 2) * H + 1) / 2 + 1;  // doubled arrays of H words, filler masks, one pad word (the
+                                                           // last word of an odd H reads one word past its doubled array)
     slot += ((W - slot) % 32 + 32) % 32;  // slot = W (mod 32): thread (g, w) falls in bank (g W + w) mod 32
     a.slot = slot;
     auto magic = [](uint32_t d) { return (uint32_t)((1ull << 32) / d) + 1u; };
@@ -442,7 +458,7 @@ int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, in
     a.s3 = ((c.bgn == 1 ? a.s4 : a.s2) + a.p3) % Zc;
     auto desc = [&](uint32_t ed, int last) {
         const int j = ed & 0xff, P = ed >> 8;
-        return (uint32_t)((j * 2 * W + (P >> 5)) * 4) << 16 | (uint32_t)last << 5 | (uint32_t)(P & 31);
+        return (uint32_t)((j * H + (P >> 5)) * 4) << 16 | (uint32_t)last << 5 | (uint32_t)(P & 31);
     };
     for (int p = 0; p < kWParts; ++p) {
         int n = 0;
@@ -462,7 +478,7 @@ int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, in
         }
         a.next[p] = (uint16_t)n;
     }
-    const int smem_bytes = a.G * (slot + nout * W) * 4;
+    const int smem_bytes = a.G * (slot + nout * H / 2) * 4 + 16;
     static bool attr_done[64] = {};
     int dev = 0;
     NRLDPC_CUDA(cudaGetDevice(&dev));
@@ -483,7 +499,7 @@ int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t
     if (B <= 0) return NRLDPC_OK;
     EncRmArgs rm;
     if (rm_in) rm = *rm_in;
-    if (cfg.Zc % 32 == 0 && (reinterpret_cast<uintptr_t>(d_ck) | reinterpret_cast<uintptr_t>(d_dn)) % 16 == 0)
+    if (cfg.Zc % 16 == 0 && cfg.Zc >= 32 && (reinterpret_cast<uintptr_t>(d_ck) | reinterpret_cast<uintptr_t>(d_dn)) % 16 == 0)
         return launch_encode_words(cfg, d_ck, B, fix_fillers, d_dn, s, rm);
     const int Wp = cfg.tiles + 1;
     const int slot_bytes = (cfg.ncols * Wp + cfg.kb * cfg.tiles + 5 * Wp) * 4;
