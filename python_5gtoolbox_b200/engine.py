@@ -6,6 +6,7 @@ stream (PyTorch is only the allocator / stream provider).  One (bgn, Zc) per cal
 transport block in the reference (py5gphy/ldpc/ldpc_info.py:62-69).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -467,11 +468,13 @@ class _PinnedBlock:
     """A block of the library's pinned host memory pool (nrldpc_host_alloc); returned to the pool when the last
     NumPy view of it is garbage-collected."""
     __slots__ = ("ptr", "nbytes", "__weakref__")
+    live_bytes = 0   # pinned bytes currently owned by NumPy arrays handed to callers
 
     def __init__(self, nbytes):
         p = ctypes.c_void_p()
         _lib.check(_lib.lib().nrldpc_host_alloc(max(int(nbytes), 1), ctypes.byref(p)), "host_alloc")
         self.ptr, self.nbytes = p.value, int(nbytes)
+        _PinnedBlock.live_bytes += self.nbytes
 
     @property
     def __array_interface__(self):
@@ -479,9 +482,16 @@ class _PinnedBlock:
 
     def __del__(self):
         try:
+            _PinnedBlock.live_bytes -= self.nbytes
             _lib.lib().nrldpc_host_free(self.ptr)
         except Exception:   # interpreter shutdown
             pass
+
+
+# A caller that keeps every returned soft buffer alive (16 HARQ processes x 23 MB is fine, a list of 10 000 results is not)
+# must not be able to page-lock the machine's memory: beyond this many live bytes results come back in ordinary (pageable)
+# NumPy memory, which every entry point accepts (staged copy).  NRLDPC_PINNED_LIMIT_MB overrides the 4 GiB default.
+_PINNED_LIMIT = int(os.environ.get("NRLDPC_PINNED_LIMIT_MB", "4096")) << 20
 
 
 def pinned_empty(shape, dtype):
@@ -489,7 +499,7 @@ def pinned_empty(shape, dtype):
     and the fused transport-block decoder stores its float64 soft buffer into it while it iterates."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
-    if n == 0:
+    if n == 0 or _PinnedBlock.live_bytes + n > _PINNED_LIMIT:
         return np.empty(shape, dtype)
     return np.asarray(_PinnedBlock(n)).view(dtype).reshape(shape)
 

@@ -136,8 +136,8 @@ class CudaBackend:
         A = K - crc_len
         poly = {"24A": 3, "24B": 4, "16": 2}[crcpoly]
         first, stride = offset + take[0], (take[1] - take[0]) if m > 1 else 1
-        fails = 0
         L_ = _lib.lib()
+        counters = torch.zeros(4, dtype=torch.int64, device=self.device)   # accumulated on the device: ONE host read per stretch
         with torch.cuda.device(self.device):
             for i0 in range(0, m, 8192):
                 mm = min(8192, m - i0)
@@ -152,14 +152,13 @@ class CudaBackend:
                                                    stride, llr.data_ptr(), s), "awgn")
                 if algo == 'BF':   # quasi-cyclic bit-flipping kernel, device-resident like the min-sum chain
                     ck, _, it = engine.decode_bf_batch(llr, Zc, bgn, L)
-                    fails += int(engine.count_errors(blk, ck, K, it)[1].item())
                 elif algo == 'BP':   # quasi-cyclic sum-product kernel: float64 arithmetic on the device-resident fp32 LLRs
                     ck, _, it = engine.decode_bp_batch(llr, Zc, bgn, L)
-                    fails += int(engine.count_errors(blk, ck, K, it)[1].item())
                 else:
                     r = engine.decode_batch(llr, Zc, bgn, L, alpha, beta, True)
-                    cnt = engine.count_errors(blk, r["ck"], K, r["iters"])
-                    fails += int(cnt[1].item())
+                    ck, it = r["ck"], r["iters"]
+                engine.count_errors(blk, ck, K, it, counters)
+        fails = int(counters[1].item())
         return fails
 
 

@@ -416,3 +416,28 @@ def test_half_precision_host_llrs(eng):
         got = eng.decode_batch(h, Zc, bgn, 10, 0.8, 0.0, True, want_info=True)
         for k in ("ck", "info", "status", "iters"):
             assert np.array_equal(got[k], want[k]), (bgn, Zc, k)
+
+
+@pytest.mark.gpu
+def test_sch_entry_points_reject_bad_arguments_and_fall_back_to_pageable(eng, monkeypatch):
+    """Inconsistent transport-block layouts raise AssertionError (the reference asserts in get_cbs_info / reshape); beyond
+    the pinned-memory cap results come back in pageable memory and are the same."""
+    rng = np.random.default_rng(3)
+    t = _tb_case(rng, 1, 384, 3, 4, 1, 0, 1.0, 0.5, 8)
+    llr = rng.normal(0, 4, int(sum(t["Er"]))).astype("f4")
+    with pytest.raises(AssertionError):   # K_apo does not match A / C
+        eng.sch_decode_host(llr, t["Er"], 1, 384, t["Ncb"], t["k0"], t["Qm"], t["K_apo"] + 1, t["A"], 5, 0.8, 0.0)
+    with pytest.raises(AssertionError):   # E not a multiple of Qm
+        bad = list(t["Er"]); bad[0] += 1; bad[1] -= 1
+        eng.sch_decode_host(llr, bad, 1, 384, t["Ncb"], t["k0"], t["Qm"], t["K_apo"], t["A"], 5, 0.8, 0.0)
+    with pytest.raises(AssertionError):   # k0 outside the circular buffer
+        eng.sch_decode_host(llr, t["Er"], 1, 384, t["Ncb"], t["Ncb"], t["Qm"], t["K_apo"], t["A"], 5, 0.8, 0.0)
+    with pytest.raises(AssertionError):   # not a 5G lifting size
+        eng.sch_decode_host(llr, t["Er"], 1, 385, t["Ncb"], t["k0"], t["Qm"], t["K_apo"], t["A"], 5, 0.8, 0.0)
+    a = eng.sch_decode_host(llr, t["Er"], 1, 384, t["Ncb"], t["k0"], t["Qm"], t["K_apo"], t["A"], 5, 0.8, 0.0)
+    from python_5gtoolbox_b200 import engine
+    monkeypatch.setattr(engine, "_PINNED_LIMIT", 0)
+    b = eng.sch_decode_host(llr, t["Er"], 1, 384, t["Ncb"], t["k0"], t["Qm"], t["K_apo"], t["A"], 5, 0.8, 0.0)
+    for k in ("tbblk", "soft", "status", "iters", "cb_err"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["tb_err"] == b["tb_err"]

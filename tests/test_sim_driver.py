@@ -33,7 +33,7 @@ class OracleBackend:
             blk = O.nr_crc_encode(inb.astype("i1"), crcpoly)
             dn = O.encode_ldpc(blk.copy(), bgn)
             llr = 2 * ((1 - 2 * dn) + nz) / 10 ** (-snr_db / 10)
-            out, ck, st, it = O.nr_decode_ldpc(llr.astype("f4").astype("f8"), Zc, bgn, L, algo, alpha, beta)
+            out, ck, st, it = O.nr_decode_ldpc(llr, Zc, bgn, L, algo, alpha, beta)   # un-rounded float64, like the reference's scripts
             fails += not np.array_equal(out, blk)
         return fails
 
