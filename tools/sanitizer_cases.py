@@ -58,3 +58,27 @@ for poly, n in (("24A", 8424), ("24B", 3000), ("16", 500)):
     chk = engine.crc_check_device(enc, poly)
     torch.cuda.synchronize()
 print("crc ok", flush=True)
+
+# round 2: sum-product kernel, fused transport-block chain (rate recovery inside the decoder, CB/TB CRC kernels, fused
+# rate-matching store of the encoder) on a specialised and a table-driven lifting size, half-precision host LLRs
+import numpy as np  # noqa: E402
+from python_5gtoolbox_b200.nr_pdsch import nr_dlsch, nr_dlsch_decode  # noqa: E402
+
+for bgn, Zc in ((1, 64), (2, 12)):
+    K, N, Nf, M = engine.dims(bgn, Zc)
+    ck = engine.random_bits(3, K, seed=5, device=dev)
+    llr = engine.awgn_llr(engine.encode_batch(ck, bgn), 2.0, seed=6)
+    engine.decode_bp_batch(llr, Zc, bgn, 4)
+    engine.decode_batch(llr.cpu().numpy().astype(np.float16), Zc, bgn, 4, 0.8, 0.0, True)
+torch.cuda.synchronize()
+print("bp / f16 ok", flush=True)
+rng = np.random.default_rng(1)
+cfg = {"L": 6, "algo": "min-sum", "alpha": 0.8, "beta": 0.0}
+for A, R, Qm, NL, G in ((30000, 700, 4, 2, 48000), (2000, 300, 2, 1, 9000)):
+    trblk = rng.integers(0, 2, A).astype("i1")
+    g = nr_dlsch.DLSCHEncode(trblk, A, Qm, R, NL, 0, 10 ** 9, G)
+    x = (4.0 * (1 - 2 * g.astype("f4"))).astype("f4")
+    st, tb, new = nr_dlsch_decode.DLSCHDecode(x, A, Qm, R, NL, 0, 10 ** 9, cfg)
+    st2, tb2, new2 = nr_dlsch_decode.DLSCHDecode(x, A, Qm, R, NL, 0, 10 ** 9, cfg, HARQ_on=True, current_LLr_dns=new)
+    assert st and st2 and np.array_equal(tb, trblk)
+print("transport-block chain ok", flush=True)
