@@ -273,6 +273,7 @@ __device__ __forceinline__ uint32_t rot2d(const uint32_t *v2w, uint32_t d)
     return __funnelshift_r(p[0], p[1], d);
 }
 
+template <bool ODD>   // ODD: Zc = 16 * odd (half-word stores into the doubled arrays)
 __global__ void __launch_bounds__(kWThreads)
 encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ ck, int B, int fix_fillers,
                     int8_t *__restrict__ dn)
@@ -284,7 +285,7 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
     // is why every store into a doubled array below is made of half words.  W = ceil(H/2) threads cover a column-block;
     // in the last word of an odd H only the low half is valid.
     const int W = a.W, H = a.H, W2 = H, kb = a.kb, nout = a.nout;
-    const bool odd = H & 1;
+    constexpr bool odd = ODD;
     const int cb0 = blockIdx.x * a.G, g_cnt = min(a.G, B - cb0);
     // per codeblock slot: D2[kb+4][H words] (systematic + core parity, doubled), L2x[4][H words] (L1 rows, doubled),
     // FM[kb-2][H half words] (filler masks, indexed like dn's half words); then OUT[G][nout][H half words]: dn packed,
@@ -483,11 +484,13 @@ int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, in
     int dev = 0;
     NRLDPC_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_done[dev]) {
-        NRLDPC_CUDA(cudaFuncSetAttribute(encode_words_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        NRLDPC_CUDA(cudaFuncSetAttribute(encode_words_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        NRLDPC_CUDA(cudaFuncSetAttribute(encode_words_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         attr_done[dev] = true;
     }
     const int grid = (B + a.G - 1) / a.G;
-    encode_words_kernel<<<grid, kWThreads, smem_bytes, s>>>(a, d_ck, B, fix_fillers, d_dn);
+    if (H & 1) encode_words_kernel<true><<<grid, kWThreads, smem_bytes, s>>>(a, d_ck, B, fix_fillers, d_dn);
+    else encode_words_kernel<false><<<grid, kWThreads, smem_bytes, s>>>(a, d_ck, B, fix_fillers, d_dn);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
 }

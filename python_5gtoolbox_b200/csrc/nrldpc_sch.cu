@@ -198,7 +198,7 @@ CopyThreads &copy_threads()
 
 void host_copy(void *dst, const void *src, size_t n)
 {
-    if (n < ((size_t)512 << 10)) { memcpy(dst, src, n); return; }
+    if (n < ((size_t)2 << 20)) { memcpy(dst, src, n); return; }   // waking the helpers costs more than a 2 MiB memcpy saves
     std::lock_guard<std::mutex> lk(g_copy_mu);
     copy_threads().copy(dst, src, n);
 }
