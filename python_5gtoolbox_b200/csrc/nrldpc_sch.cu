@@ -707,16 +707,29 @@ extern "C" int nrldpc_sch_decode_host(const void *llr_g, int in_f64, int C, int 
             soft_copy = true;
         }
     }
-    if (cur) NRLDPC_CUDA(d_cur.alloc(nsoft, s));
+    // the soft buffer of the earlier transmissions: read by the decoder's prologue straight from the caller's pinned host
+    // memory (zero-copy: the reads go host -> device while the new soft buffer is stored device -> host, the two directions
+    // of the link; NRLDPC_CUR_H2D=1: copied to the device first, for A/B timing); pageable memory is staged and copied
+    static const bool cur_h2d = getenv("NRLDPC_CUR_H2D") != nullptr;
+    const double *cur_dev = nullptr;
+    if (cur) {
+        void *dp = nullptr;
+        if (!cur_h2d && is_pinned(cur) && cudaHostGetDevicePointer(&dp, const_cast<double *>(cur), 0) == cudaSuccess) cur_dev = (const double *)dp;
+        else {
+            cudaGetLastError();
+            NRLDPC_CUDA(d_cur.alloc(nsoft, s));
+            cur_dev = d_cur.as<double>();
+        }
+    }
     mark();
     if (int rc = h2d_async(d_E.p, E, (size_t)C * 4, s)) return rc;
     if (int rc = h2d_async(d_off.p, off.data(), (size_t)C * 8, s)) return rc;
     if (int rc = h2d_async(d_in.p, llr_g, (size_t)total * esz, s)) return rc;
-    if (cur) if (int rc = h2d_async(d_cur.p, cur, nsoft, s)) return rc;
+    if (cur && d_cur.p) if (int rc = h2d_async(d_cur.p, cur, nsoft, s)) return rc;
     mark();
     uint8_t *sm = d_small.as<uint8_t>();
     int rc = nrldpc_sch_decode(d_in.p, in_f64, C, bgn, Zc, Ncb, k0, Qm, K_apo, d_E.as<int32_t>(), d_off.as<long long>(),
-                               cur ? d_cur.as<double>() : nullptr, soft_dev, max_iter, alpha, beta, A, nullptr, d_tb.as<int8_t>(), sm,
+                               cur_dev, soft_dev, max_iter, alpha, beta, A, nullptr, d_tb.as<int8_t>(), sm,
                                sm + o_cb, sm + o_st, reinterpret_cast<int32_t *>(sm + o_it), s);
     if (rc != NRLDPC_OK) { cudaStreamSynchronize(s); return rc; }
     mark();
