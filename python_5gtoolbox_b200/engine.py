@@ -567,7 +567,7 @@ def encode_ratematch_host(cbs, bgn, Zc, Ncb, k0, Qm, E_list, fix_fillers=True):
     assert cbs.dtype == np.int8 and cbs.flags.c_contiguous and cbs.ndim == 2 and cbs.shape[0] == E.size
     K, N, Nf, M = dims(bgn, Zc)
     assert cbs.shape[1] == K
-    g = np.empty(int(E.sum(dtype=np.int64)), np.int8)
+    g = pinned_empty((int(E.sum(dtype=np.int64)),), np.int8)   # DMA target: no staged copy on the way back
     _lib.check(_lib.lib().nrldpc_encode_ratematch_host(cbs.ctypes.data, E.size, bgn, int(Zc), int(bool(fix_fillers)), int(Ncb), int(k0),
                                                        int(Qm), E.ctypes.data, g.ctypes.data), "encode_ratematch")
     return g
@@ -578,7 +578,7 @@ def sch_encode_host(trblk, C, bgn, Zc, Ncb, k0, Qm, E_list):
     trblk int8 [A] -> int8 [sum E] (py5gphy/nr_pdsch/nr_dlsch.py:12-74)."""
     E = np.ascontiguousarray(E_list, np.int32).reshape(-1)
     t = np.ascontiguousarray(trblk, np.int8).reshape(-1)
-    g = np.empty(int(E.sum(dtype=np.int64)), np.int8)
+    g = pinned_empty((int(E.sum(dtype=np.int64)),), np.int8)   # DMA target: no staged copy on the way back
     _lib.check(_lib.lib().nrldpc_sch_encode_host(t.ctypes.data, t.size, int(C), bgn, int(Zc), int(Ncb), int(k0), int(Qm),
                                                  E.ctypes.data, g.ctypes.data), "sch_encode")
     return g
