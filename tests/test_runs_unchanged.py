@@ -128,3 +128,38 @@ def test_replay_reference_call_sequences(scenario, tmp_path):
                 assert _same(args[j], _unpack(after, arrays)), (ctx, "argument", j)
         n += 1
     assert n == len(sc["calls"]) and n > 0
+
+
+def test_matplotlib_stub_and_workdir(tmp_path):
+    """CPU: the matplotlib stand-in accepts the reference's plotting calls and does not break module-protocol probes (a stub
+    that answered `__file__` / `__spec__` made `import torch` fail on the GPU box); the scratch directory of
+    run_reference_script mirrors a reference root, with a writable out/ that holds copies of the stored results."""
+    import importlib
+    import sys
+    from python_5gtoolbox_b200 import _mpl_stub, run_reference_script
+    had = "matplotlib" in sys.modules
+    stubbed = _mpl_stub.install()
+    import matplotlib.pyplot as plt
+    if stubbed:
+        fig = plt.figure()
+        plt.plot([1, 2], [3, 4], marker=".", label="x")
+        plt.savefig("nowhere.png")
+        plt.close(fig)
+        import matplotlib
+        with pytest.raises(AttributeError):
+            matplotlib.__file__
+        assert importlib.util.find_spec("torch") is not None
+        import torch  # noqa: F401  (must import with the stub in place)
+        if not had:
+            del sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"]
+    ref = tmp_path / "ref"
+    (ref / "py5gphy").mkdir(parents=True)
+    (ref / "scripts").mkdir()
+    (ref / "out").mkdir()
+    (ref / "out" / "stored.pickle").write_bytes(b"x")
+    wd = run_reference_script.make_workdir(str(ref), str(tmp_path / "wd"))
+    assert os.path.islink(os.path.join(wd, "py5gphy")) and os.path.islink(os.path.join(wd, "scripts"))
+    assert not os.path.islink(os.path.join(wd, "out")) and os.path.isfile(os.path.join(wd, "out", "stored.pickle"))
+    with open(os.path.join(wd, "out", "new.pickle"), "wb") as f:   # writable, and the reference's own out/ is untouched
+        f.write(b"y")
+    assert sorted(os.listdir(ref / "out")) == ["stored.pickle"]
