@@ -441,3 +441,31 @@ def test_sch_entry_points_reject_bad_arguments_and_fall_back_to_pageable(eng, mo
     for k in ("tbblk", "soft", "status", "iters", "cb_err"):
         assert np.array_equal(a[k], b[k]), k
     assert a["tb_err"] == b["tb_err"]
+
+
+@pytest.mark.gpu
+def test_ticket_queue_survives_ring_wraparound(eng):
+    """The early-termination kernels draw a per-launch ticket counter from a ring of 4096 whose start values the host tracks
+    (no device state is reset between launches).  More launches than the ring has slots, on two streams: every launch
+    must decode every codeblock exactly once -- identical outputs throughout."""
+    import torch
+    bgn, Zc, B = 1, 384, 2 * 148 + 17               # >= 2 codeblocks per persistent CTA: the ticket queue is in use
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    ck = eng.random_bits(B, K, seed=31, device="cuda")
+    llr = eng.awgn_llr(eng.encode_batch(ck, bgn), 2.0, seed=32)
+    ref = eng.decode_batch(llr, Zc, bgn, 6, 0.8, 0.0, True, want_ck=False, want_info=True)
+    torch.cuda.synchronize()
+    want = (ref["info"].clone(), ref["iters"].clone(), ref["status"].clone())
+    side = torch.cuda.Stream()
+    last = []
+    for k in range(4300):
+        if k % 2:
+            with torch.cuda.stream(side):
+                r = eng.decode_batch(llr, Zc, bgn, 6, 0.8, 0.0, True, want_ck=False, want_info=True)
+        else:
+            r = eng.decode_batch(llr, Zc, bgn, 6, 0.8, 0.0, True, want_ck=False, want_info=True)
+        if k % 430 == 0 or k >= 4296:
+            last.append(r)
+    torch.cuda.synchronize()
+    for r in last:
+        assert torch.equal(r["info"], want[0]) and torch.equal(r["iters"], want[1]) and torch.equal(r["status"], want[2])
