@@ -26,6 +26,13 @@
 #include "nrldpc_common.cuh"
 #include "nrldpc_raterecover.cuh"
 
+// inside a host-buffer entry point, once work has been queued on stream `s`: fail only after the stream has drained, so that
+// no copy from / into the caller's buffers is still in flight when the function returns
+#define NRLDPC_TRY_SYNC(expr)                                         \
+    do {                                                              \
+        if (int rc__ = (expr)) { cudaStreamSynchronize(s); return rc__; } \
+    } while (0)
+
 namespace nrldpc {
 
 // ------------------------------------------------------------------ pinned host memory: pool + staging
@@ -618,10 +625,10 @@ extern "C" int nrldpc_sch_recover_host(const void *llr_g, int in_f64, int C, int
     NRLDPC_CUDA(d_off.alloc((size_t)C * 8, s));
     NRLDPC_CUDA(d_soft.alloc(nsoft, s));
     if (cur) NRLDPC_CUDA(d_cur.alloc(nsoft, s));
-    if (int rc = h2d_async(d_in.p, llr_g, (size_t)total * esz, s)) return rc;
-    if (int rc = h2d_async(d_E.p, E, (size_t)C * 4, s)) return rc;
-    if (int rc = h2d_async(d_off.p, off.data(), (size_t)C * 8, s)) return rc;
-    if (cur) if (int rc = h2d_async(d_cur.p, cur, nsoft, s)) return rc;
+    NRLDPC_TRY_SYNC(h2d_async(d_in.p, llr_g, (size_t)total * esz, s));
+    NRLDPC_TRY_SYNC(h2d_async(d_E.p, E, (size_t)C * 4, s));
+    NRLDPC_TRY_SYNC(h2d_async(d_off.p, off.data(), (size_t)C * 8, s));
+    if (cur) NRLDPC_TRY_SYNC(h2d_async(d_cur.p, cur, nsoft, s));
     int rc = nrldpc_sch_recover(d_in.p, in_f64, C, N, Ncb, k0, Qm, K_apo - 2 * Zc, K - 2 * Zc, d_E.as<int32_t>(), d_off.as<long long>(),
                                 cur ? d_cur.as<double>() : nullptr, d_soft.as<double>(), nullptr, s);
     if (rc == NRLDPC_OK) rc = d2h_sync(soft, d_soft.p, nsoft, s);
@@ -722,19 +729,22 @@ extern "C" int nrldpc_sch_decode_host(const void *llr_g, int in_f64, int C, int 
         }
     }
     mark();
-    if (int rc = h2d_async(d_E.p, E, (size_t)C * 4, s)) return rc;
-    if (int rc = h2d_async(d_off.p, off.data(), (size_t)C * 8, s)) return rc;
-    if (int rc = h2d_async(d_in.p, llr_g, (size_t)total * esz, s)) return rc;
-    if (cur && d_cur.p) if (int rc = h2d_async(d_cur.p, cur, nsoft, s)) return rc;
+    // from here on copies from / kernels storing into the caller's buffers may be in flight: no return without a
+    // synchronisation of the stream
+    int rc = h2d_async(d_E.p, E, (size_t)C * 4, s);
+    if (rc == NRLDPC_OK) rc = h2d_async(d_off.p, off.data(), (size_t)C * 8, s);
+    if (rc == NRLDPC_OK) rc = h2d_async(d_in.p, llr_g, (size_t)total * esz, s);
+    if (rc == NRLDPC_OK && cur && d_cur.p) rc = h2d_async(d_cur.p, cur, nsoft, s);
+    if (rc != NRLDPC_OK) { cudaStreamSynchronize(s); return rc; }
     mark();
     uint8_t *sm = d_small.as<uint8_t>();
-    int rc = nrldpc_sch_decode(d_in.p, in_f64, C, bgn, Zc, Ncb, k0, Qm, K_apo, d_E.as<int32_t>(), d_off.as<long long>(),
+    rc = nrldpc_sch_decode(d_in.p, in_f64, C, bgn, Zc, Ncb, k0, Qm, K_apo, d_E.as<int32_t>(), d_off.as<long long>(),
                                cur_dev, soft_dev, max_iter, alpha, beta, A, nullptr, d_tb.as<int8_t>(), sm,
                                sm + o_cb, sm + o_st, reinterpret_cast<int32_t *>(sm + o_it), s);
     if (rc != NRLDPC_OK) { cudaStreamSynchronize(s); return rc; }
     mark();
     void *h_small = nullptr;
-    NRLDPC_CUDA(pinned_pool().get(nsmall, &h_small));
+    if (cudaError_t ea = pinned_pool().get(nsmall, &h_small)) { cudaStreamSynchronize(s); return cuda_fail(ea, "cudaHostAlloc(results)"); }
     cudaError_t e = cudaMemcpyAsync(h_small, sm, nsmall, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && soft_copy) {
         rc = d2h_sync(soft, d_soft.p, nsoft, s);
@@ -802,7 +812,7 @@ extern "C" int nrldpc_sch_segment_host(const int8_t *trblk, int A, int C, int K,
     NRLDPC_CUDA(d_tb.alloc((size_t)A, s));
     NRLDPC_CUDA(d_cbs.alloc((size_t)C * K, s));
     NRLDPC_CUDA(d_acc.alloc(8, s));
-    if (int rc = h2d_async(d_tb.p, trblk, (size_t)A, s)) return rc;
+    NRLDPC_TRY_SYNC(h2d_async(d_tb.p, trblk, (size_t)A, s));
     int rc = sch_segment_impl(d_tb.as<int8_t>(), A, C, K, d_cbs.as<int8_t>(), d_acc.as<uint32_t>(), s);
     uint32_t h_acc[2] = {0, 0};
     if (rc == NRLDPC_OK && cudaMemcpyAsync(h_acc, d_acc.p, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync");
@@ -843,8 +853,8 @@ int encode_chain_host(const int8_t *trblk, int A, int8_t *cbs, int C, int bgn, i
     NRLDPC_CUDA(d_E.alloc((size_t)C * 4, s));
     NRLDPC_CUDA(d_off.alloc((size_t)C * 8, s));
     NRLDPC_CUDA(d_g.alloc((size_t)total, s));
-    if (int rc = h2d_async(d_E.p, E, (size_t)C * 4, s)) return rc;
-    if (int rc = h2d_async(d_off.p, off.data(), (size_t)C * 8, s)) return rc;
+    NRLDPC_TRY_SYNC(h2d_async(d_E.p, E, (size_t)C * 4, s));
+    NRLDPC_TRY_SYNC(h2d_async(d_off.p, off.data(), (size_t)C * 8, s));
     int rc = NRLDPC_OK;
     if (trblk) {
         NRLDPC_CUDA(d_tb.alloc((size_t)A, s));
