@@ -92,3 +92,24 @@ def test_table_checksums():
     want = {(1, 0): "b68fc6c3", (1, 1): "f5948ae1", (1, 6): "6f5f6990", (2, 0): "094b454c", (2, 2): "bf5a7060", (2, 7): "ff802df5"}
     for (bgn, s), crc in want.items():
         assert "%08x" % zlib.crc32(ldpc_info.base_graph(bgn, s).astype("<i2").tobytes()) == crc
+
+
+def test_bench_reference_arm_contract():
+    """CPU: `bench.py --impl reference` (the oracle port on the host cores) prints ONE JSON line with the contract's keys,
+    honours --steps inside its time budget and needs no GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, REF_BUDGET_S="60", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "decoded_info_gbit_per_s" and d["unit"] == "Gbit/s" and d["higher_is_better"]
+    assert d["steps"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "BG1 Zc=384" in d["config"]["workload"]
