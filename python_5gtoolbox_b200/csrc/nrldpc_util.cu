@@ -71,47 +71,64 @@ __global__ void random_bits_kernel(int8_t *bits, long long rows, long long cols,
     }
 }
 
-__global__ void awgn_llr_kernel(const int8_t *__restrict__ dn, long long rows, long long cols, float sigma, float scale,
-                                unsigned long long seed, unsigned long long ctr0, long long first_id, long long id_stride,
-                                float *__restrict__ llr)
+// A CTA walks whole rows (one long row: stretches of kAwgnStretch Philox blocks), so that the 64-bit counter base and the row
+// pointers are formed once per stretch and everything per Philox block is 32-bit arithmetic.  The counter of block blk of row j
+// is ctr0 + (first_id + j * id_stride) * bpr + blk, whatever the launch geometry.
+constexpr unsigned kAwgnStretch = 8192;
+
+__global__ void __launch_bounds__(256)
+awgn_llr_kernel(const int8_t *__restrict__ dn, long long rows, long long cols, float sigma, float scale,
+                unsigned long long seed, unsigned long long ctr0, long long first_id, long long id_stride,
+                float *__restrict__ llr)
 {
-    const long long bpr = (cols + 3) / 4, nblk = rows * bpr;  // one Philox block = 4 normals
+    const unsigned long long bpr = (unsigned long long)(cols + 3) / 4;  // one Philox block = 4 normals
     const bool vec4 = (cols % 4 == 0) && (reinterpret_cast<uintptr_t>(dn) % 4 == 0) && (reinterpret_cast<uintptr_t>(llr) % 16 == 0);
-    const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long srow = stride / bpr, sblk = stride - srow * bpr;
-    long long row = t0 / bpr, blk = t0 - row * bpr;
-    for (long long t = t0; t < nblk; t += stride, row += srow, blk += sblk) {
-        if (blk >= bpr) { blk -= bpr; ++row; }
-        const uint4 x = philox_at(seed ^ 0x9E3779B97F4A7C15ull, ctr0 + (unsigned long long)((first_id + row * id_stride) * bpr + blk));
-        // Box-Muller on two uniform pairs
-        const float u0 = ((x.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((x.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float u2 = ((x.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((x.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        // Box-Muller on the special-function unit: lg2 / sqrt / sin / cos are one MUFU instruction each (relative error
-        // ~2^-21 on the radius, absolute error ~2^-21 on the angle part: far below the Monte-Carlo resolution of a BLER
-        // point).  The software sincospif + IEEE sqrtf this replaces were ~40 % of the kernel's instructions.
-        const float r0 = sqrt_approx(-2.0f * __logf(u0)), r1 = sqrt_approx(-2.0f * __logf(u2));
-        float s0, c0, s1, c1;
-        __sincosf(6.28318530717958647692f * u1, &s0, &c0);
-        __sincosf(6.28318530717958647692f * u3, &s1, &c1);
-        const float n[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
-        const long long base = blk * 4;
-        if (vec4 && base + 4 <= cols) {
-            const char4 d4 = *reinterpret_cast<const char4 *>(dn + row * cols + base);
-            const int d[4] = {d4.x, d4.y, d4.z, d4.w};
-            float4 o;
-            float *op = &o.x;
+    const unsigned long long spr = (bpr + kAwgnStretch - 1) / kAwgnStretch, nstretch = (unsigned long long)rows * spr;
+    const uint2 key = make_uint2((uint32_t)(seed ^ 0x9E3779B97F4A7C15ull), (uint32_t)((seed ^ 0x9E3779B97F4A7C15ull) >> 32));
+    const float sig_scale = sigma * scale;  // LLR = scale * (en + sigma n) = scale * en + (sigma scale) * n
+    for (unsigned long long st = blockIdx.x; st < nstretch; st += gridDim.x) {
+        const unsigned long long row = spr == 1 ? st : st / spr, s0 = (st - row * spr) * kAwgnStretch;
+        const unsigned nb = (unsigned)min((unsigned long long)kAwgnStretch, bpr - s0);
+        const unsigned long long cbase = ctr0 + (unsigned long long)(first_id + (long long)row * id_stride) * bpr + s0;
+        const int8_t *d = dn + row * cols + s0 * 4;
+        float *o = llr + row * cols + s0 * 4;
+        const long long left = cols - (long long)s0 * 4;  // values of this row from the stretch on
+        for (unsigned b = threadIdx.x; b < nb; b += blockDim.x) {
+            const unsigned long long c = cbase + b;
+            const uint4 x = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x4c445043u, 0u), key);
+            // Box-Muller on two uniform pairs, on the special-function unit: lg2 / sqrt / sin / cos are one MUFU instruction
+            // each (relative error ~2^-21 on the radius, absolute ~2^-21 on the angle part: far below the Monte-Carlo
+            // resolution of a BLER point)
+            const float u0 = ((x.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((x.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            const float u2 = ((x.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((x.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
+            const float r0 = sqrt_approx(-2.0f * __logf(u0)), r1 = sqrt_approx(-2.0f * __logf(u2));
+            float s0f, c0f, s1f, c1f;
+            __sincosf(6.28318530717958647692f * u1, &s0f, &c0f);
+            __sincosf(6.28318530717958647692f * u3, &s1f, &c1f);
+            const float n[4] = {r0 * c0f, r0 * s0f, r1 * c1f, r1 * s1f};
+            if (vec4) {
+                // :252-257  en = 1 - 2 dn ; fn = en + N(0, sigma) ; LLR = 2 fn / sigma^2 ; a -1 filler is sent as LLR 0
+                const uint32_t d4 = *reinterpret_cast<const uint32_t *>(d + 4 * b);
+                float4 v;
+                float *vp = &v.x;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = d[i] < 0 ? 0.0f : scale * ((1.0f - 2.0f * (float)d[i]) + sigma * n[i]);
-            *reinterpret_cast<float4 *>(llr + row * cols + base) = o;
-            continue;
-        }
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t byte = (d4 >> (8 * i)) & 0xffu;
+                    // scale * (+-1) by flipping the sign bit with the data bit; fused multiply-add for the noise term
+                    const float en = __uint_as_float(__float_as_uint(scale) ^ (byte << 31));
+                    vp[i] = (byte & 0x80u) ? 0.0f : __fmaf_rn(sig_scale, n[i], en);
+                }
+                *reinterpret_cast<float4 *>(o + 4 * b) = v;
+            } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (base + i < cols) {
-                const int d = dn[row * cols + base + i];
-                // :252-257  en = 1 - 2 dn ; fn = en + N(0, sigma) ; LLR = 2 fn / sigma^2
-                llr[row * cols + base + i] = d < 0 ? 0.0f : scale * ((1.0f - 2.0f * (float)d) + sigma * n[i]);
+                for (int i = 0; i < 4; ++i)
+                    if ((long long)4 * b + i < left) {
+                        const int dv = d[4 * b + i];
+                        const float en = dv ? -scale : scale;
+                        o[4 * b + i] = dv < 0 ? 0.0f : __fmaf_rn(sig_scale, n[i], en);
+                    }
             }
+        }
     }
 }
 
@@ -241,6 +258,12 @@ static int grid_for(long long nblk, int per_sm)
     return (int)(g > 148LL * per_sm ? 148LL * per_sm : (g < 1 ? 1 : g));
 }
 
+static int awgn_grid(long long rows, long long cols)
+{
+    const long long bpr = (cols + 3) / 4, spr = (bpr + 8191) / 8192, n = rows * spr;
+    return (int)(n > 148LL * 8 ? 148LL * 8 : (n < 1 ? 1 : n));
+}
+
 extern "C" int nrldpc_random_bits_rows(int8_t *d_bits, long long rows, long long cols, unsigned long long seed,
                                        long long first_id, long long id_stride, void *stream)
 {
@@ -264,7 +287,7 @@ extern "C" int nrldpc_awgn_llr_rows(const int8_t *d_dn, long long rows, long lon
 {
     if (rows <= 0 || cols <= 0) return NRLDPC_OK;
     const double sigma = pow(10.0, -(double)snr_db / 20.0), np = pow(10.0, -(double)snr_db / 10.0);
-    awgn_llr_kernel<<<grid_for(rows * ((cols + 3) / 4), 32), 256, 0, (cudaStream_t)stream>>>(
+    awgn_llr_kernel<<<awgn_grid(rows, cols), 256, 0, (cudaStream_t)stream>>>(
         d_dn, rows, cols, (float)sigma, (float)(2.0 / np), seed, 0, first_id, id_stride, d_llr);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
@@ -275,7 +298,7 @@ extern "C" int nrldpc_awgn_llr(const int8_t *d_dn, long long count, float snr_db
 {
     if (count <= 0) return NRLDPC_OK;
     const double sigma = pow(10.0, -(double)snr_db / 20.0), np = pow(10.0, -(double)snr_db / 10.0);
-    awgn_llr_kernel<<<grid_for((count + 3) / 4, 32), 256, 0, (cudaStream_t)stream>>>(
+    awgn_llr_kernel<<<awgn_grid(1, count), 256, 0, (cudaStream_t)stream>>>(
         d_dn, 1, count, (float)sigma, (float)(2.0 / np), seed, offset, 0, 0, d_llr);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
