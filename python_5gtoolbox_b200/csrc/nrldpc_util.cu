@@ -208,16 +208,24 @@ __host__ __device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b, 
 // instead of a square-and-multiply chain of ~40)
 struct CrcPow { uint32_t p[kCrcBlockThreads]; };
 
-template <int T>
+// STAGE: the block of bits is first copied into shared memory with coalesced loads (a thread walking its own chunk of a
+// global row reads one byte per 32-byte sector and instruction: 0.21 ms per 16 384 codeblock payloads, 5x the staged version)
+template <int T, bool STAGE>
 __global__ void __launch_bounds__(T)
 crc_block_kernel(const __grid_constant__ CrcPow pw, const int8_t *__restrict__ in, int A, int L, uint32_t poly, int mode,
                  int8_t *__restrict__ out, uint8_t *__restrict__ err)
 {
     constexpr int kCrcBlockThreads = T;
+    extern __shared__ int8_t s_x[];
     __shared__ uint32_t s_part[kCrcBlockThreads / 32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int len_in = mode ? A + L : A;
     const int8_t *x = in + (size_t)b * len_in;
+    if (STAGE) {
+        for (int k = tid; k < len_in; k += kCrcBlockThreads) s_x[k] = x[k];
+        __syncthreads();
+        x = s_x;
+    }
     const uint32_t mask = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
     const int chunk = (A + kCrcBlockThreads - 1) / kCrcBlockThreads;
     const int k0 = min(tid * chunk, A), k1 = min(k0 + chunk, A);
@@ -358,7 +366,9 @@ static void crc_block_launch(const int8_t *d_in, int B, int A, int L, uint32_t p
 {
     CrcPow pw;
     crc_pow_table(A, L, poly, T, &pw);
-    crc_block_kernel<T><<<B, T, 0, s>>>(pw, d_in, A, L, poly, mode, d_out, d_err);
+    const int len_in = mode ? A + L : A;
+    if (len_in <= 40 * 1024) crc_block_kernel<T, true><<<B, T, len_in, s>>>(pw, d_in, A, L, poly, mode, d_out, d_err);
+    else crc_block_kernel<T, false><<<B, T, 0, s>>>(pw, d_in, A, L, poly, mode, d_out, d_err);
 }
 
 extern "C" int nrldpc_crc_encode(const int8_t *d_in, int B, int A, int poly_id, int8_t *d_out, void *stream)
