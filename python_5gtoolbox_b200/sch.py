@@ -67,7 +67,8 @@ def dlsch_encode(trblk, TBSize, Qm, coderateby1024, num_of_layers, rv, Ncb_of, G
     return g_seq
 
 
-def sch_decode(LLr, G, TBSize, Qm, coderateby1024, num_of_layers, rv, Ncb_of, LDPC_decoder_config, HARQ_on, current_LLr_dns):
+def sch_decode(LLr, G, TBSize, Qm, coderateby1024, num_of_layers, rv, Ncb_of, LDPC_decoder_config, HARQ_on, current_LLr_dns,
+               soft_buffer=True):
     """De-rate-matching, HARQ combining, LDPC decoding, CB/TB CRC for all codeblocks of a transport block
     (py5gphy/nr_pdsch/nr_dlsch_decode.py:13-109, py5gphy/nr_pusch/nr_ulsch_decode.py:13-110).
     G sizes the codeblocks (get_Er_ldpc), Ncb_of(C, N) gives the circular-buffer length.  Returns (tb_ok, tbblk int8[A],
@@ -89,8 +90,9 @@ def sch_decode(LLr, G, TBSize, Qm, coderateby1024, num_of_layers, rv, Ncb_of, LD
     cfg = LDPC_decoder_config
     algo = cfg["algo"]
     if algo == 'min-sum':
-        r = engine.sch_decode_host(x, Er_list, bgn, Zc, Ncb, k0, Qm, K_apo, A, cfg["L"], cfg["alpha"], cfg["beta"], cur=cur)
-        return r["tb_err"] == 0, r["tbblk"], r["soft"]
+        r = engine.sch_decode_host(x, Er_list, bgn, Zc, Ncb, k0, Qm, K_apo, A, cfg["L"], cfg["alpha"], cfg["beta"], cur=cur,
+                                   want_soft=soft_buffer)
+        return r["tb_err"] == 0, r["tbblk"], (r["soft"] if soft_buffer else np.array([]))
     new_LLr_dns = engine.sch_recover_host(x, Er_list, bgn, Zc, Ncb, k0, Qm, K_apo, cur=cur)
     if algo == 'BF':
         ck, _, _ = engine.decode_bf_batch(new_LLr_dns, Zc, bgn, cfg["L"])

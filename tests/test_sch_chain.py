@@ -469,3 +469,22 @@ def test_ticket_queue_survives_ring_wraparound(eng):
     torch.cuda.synchronize()
     for r in last:
         assert torch.equal(r["info"], want[0]) and torch.equal(r["iters"], want[1]) and torch.equal(r["status"], want[2])
+
+
+@pytest.mark.gpu
+def test_dlsch_decode_without_soft_buffer(eng, sch_golden):
+    """The keyword-only extra soft_buffer=False (default True = the reference's return value): same status and bits."""
+    from python_5gtoolbox_b200.nr_pdsch import nr_dlsch_decode
+    n = 0
+    for name, d in sch_golden.items():
+        if str(d["link"]) != "dl" or ["min-sum", "BP", "BF"][int(d["cfg"][1])] != "min-sum":
+            continue
+        A, R, Qm, NL, TBS_LBRM, G, ntx = (int(x) for x in d["meta"])
+        cfg = {"L": int(d["cfg"][0]), "algo": "min-sum", "alpha": float(d["cfg"][2]), "beta": float(d["cfg"][3])}
+        llr = d["llr_0"].astype(np.float64)
+        rv = int(d["rvs"][0])
+        st, tb, new = nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, rv, TBS_LBRM, cfg)
+        st2, tb2, new2 = nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, rv, TBS_LBRM, cfg, soft_buffer=False)
+        assert st2 == st and np.array_equal(tb2, tb) and new2.size == 0 and new.size > 0
+        n += 1
+    assert n >= 2

@@ -45,7 +45,15 @@ for name, A, R, Qm, NL, G in cases:
     for _ in range(reps):   # retransmission: HARQ combining with the soft buffer of the previous call
         st2, tb2, new2 = nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, 0, TBS_LBRM, cfg, HARQ_on=True, current_LLr_dns=new)
     t_harq = (time.perf_counter() - t0) / reps
-    print(f"   float64 LLRs in: {t_dec64 * 1e3:.2f} ms; with HARQ combining (soft buffer in and out): {t_harq * 1e3:.2f} ms")
+    for _ in range(3):
+        nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, 0, TBS_LBRM, cfg, soft_buffer=False)
+    t0 = time.perf_counter()
+    for _ in range(reps):   # keyword-only extra: no soft buffer handed back
+        st3, tb3, _ = nr_dlsch_decode.DLSCHDecode(llr, A, Qm, R, NL, 0, TBS_LBRM, cfg, soft_buffer=False)
+    t_nosoft = (time.perf_counter() - t0) / reps
+    assert st3 == st and np.array_equal(tb3, tb)
+    print(f"   float64 LLRs in: {t_dec64 * 1e3:.2f} ms; with HARQ combining (soft buffer in and out): {t_harq * 1e3:.2f} ms; "
+          f"soft_buffer=False: {t_nosoft * 1e3:.2f} ms")
     for _ in range(3):   # warm-up with the previous result alive, like the timed loop (pinned pool: two blocks per size)
         g2 = nr_dlsch.DLSCHEncode(trblk, A, Qm, R, NL, 0, TBS_LBRM, G)
     t0 = time.perf_counter()
