@@ -567,23 +567,31 @@ int nrldpc_decode_bf_host(const double *llr, int B, int bgn, int Zc, int max_ite
     if (!c) return NRLDPC_EINVAL;
     if (B < 0 || max_iter < 0 || !llr || !ck) { set_error("decode_bf: bad argument"); return NRLDPC_EINVAL; }
     if (B == 0) return NRLDPC_OK;
-    // chunks of <= 256 MB of LLRs through scratch buffers on the default stream
+    // chunks of <= 256 MB of LLRs on this thread's stream: staged copy in, kernel, one copy of the decisions and one of
+    // {iters, status} out per chunk (a per-codeblock caller pays one synchronisation, not four blocking copies)
+    cudaStream_t s;
+    if (int rc = host_stream(&s)) return rc;
     const size_t per_cb = (size_t)c->N * 8;
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)256 << 20) / per_cb));
-    DevBuf d_llr, d_ck, d_st, d_it;
-    NRLDPC_CUDA(d_llr.alloc((size_t)chunk * per_cb));
-    NRLDPC_CUDA(d_ck.alloc((size_t)chunk * c->Nfull));
-    NRLDPC_CUDA(d_st.alloc((size_t)chunk));
-    NRLDPC_CUDA(d_it.alloc((size_t)chunk * 4));
+    DevBuf d_llr, d_ck, d_small;
+    NRLDPC_CUDA(d_llr.alloc((size_t)chunk * per_cb, s));
+    NRLDPC_CUDA(d_ck.alloc((size_t)chunk * c->Nfull, s));
+    NRLDPC_CUDA(d_small.alloc((size_t)chunk * 5, s));   // iters int32 [chunk], then status uint8 [chunk]
+    std::vector<uint8_t> h_small((size_t)chunk * 5);
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
-        NRLDPC_CUDA(cudaMemcpy(d_llr.p, llr + (size_t)b0 * c->N, (size_t)nb * per_cb, cudaMemcpyHostToDevice));
-        if (int rc = launch_bf_qc(*c, d_llr.p, 1, nb, max_iter, d_ck.as<int8_t>(), d_st.as<uint8_t>(),
-                                  d_it.as<int32_t>(), 0))
-            return rc;
-        NRLDPC_CUDA(cudaMemcpy(ck + (size_t)b0 * c->Nfull, d_ck.p, (size_t)nb * c->Nfull, cudaMemcpyDeviceToHost));
-        if (status) NRLDPC_CUDA(cudaMemcpy(status + b0, d_st.p, (size_t)nb, cudaMemcpyDeviceToHost));
-        if (iters) NRLDPC_CUDA(cudaMemcpy(iters + b0, d_it.p, (size_t)nb * 4, cudaMemcpyDeviceToHost));
+        int32_t *d_it = d_small.as<int32_t>();
+        uint8_t *d_st = d_small.as<uint8_t>() + (size_t)chunk * 4;
+        int rc = h2d_async(d_llr.p, llr + (size_t)b0 * c->N, (size_t)nb * per_cb, s);
+        if (rc == NRLDPC_OK) rc = launch_bf_qc(*c, d_llr.p, 1, nb, max_iter, d_ck.as<int8_t>(), d_st, d_it, s);
+        if (rc == NRLDPC_OK && (status || iters) &&
+            cudaMemcpyAsync(h_small.data(), d_small.p, (size_t)chunk * 5, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(D2H)");
+        if (rc == NRLDPC_OK) rc = d2h_sync(ck + (size_t)b0 * c->Nfull, d_ck.p, (size_t)nb * c->Nfull, s);  // synchronises the stream
+        else cudaStreamSynchronize(s);
+        if (rc != NRLDPC_OK) return rc;
+        if (iters) memcpy(iters + b0, h_small.data(), (size_t)nb * 4);
+        if (status) memcpy(status + b0, h_small.data() + (size_t)chunk * 4, (size_t)nb);
     }
     return NRLDPC_OK;
 }

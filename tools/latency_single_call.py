@@ -41,3 +41,12 @@ assert st and np.array_equal(tb, trblk)
 print(f"UL-SCH TB (A={A}, Zc={Zc}, C={cbs.shape[0]}, G={G}): CRC+segment {timeit(lambda: nr_ulsch.ULSCH_Crc_CodeBlockSegment(trblk, A, R)):.3f} ms, "
       f"encode+ratematch {timeit(lambda: nr_ulsch.ULSCH_encoding_ratematch(cbs.copy(), Zc, bgn, Qm, G, NL, 0)):.3f} ms, "
       f"ULSCH_decoding {timeit(lambda: nr_ulsch_decode.ULSCH_decoding(llr, A, R, Qm, G, NL, 0, cfg)):.3f} ms")
+# the per-codeblock loop of scripts/sim_ldpc_decoder_bf.py (Zc = 10, BG1): test vector + bit-flipping decode per pass
+from python_5gtoolbox_b200 import crc  # noqa: E402
+np.random.seed(1)
+blk, dn, llr = nr_ldpc_decode.for_test_5g_ldpc_encoder(10, 1, 4.0)
+bits = rng.integers(0, 2, 196).astype("i1")
+print(f"Zc=10 BG1: for_test_5g_ldpc_encoder {timeit(lambda: nr_ldpc_decode.for_test_5g_ldpc_encoder(10, 1, 4.0), 200):.3f} ms "
+      f"(crc.nr_crc_encode {timeit(lambda: crc.nr_crc_encode(bits, '24A'), 200):.3f}, encode_ldpc {timeit(lambda: nr_ldpc_encode.encode_ldpc(blk.copy(), 1), 200):.3f}), "
+      f"nr_decode_ldpc BF L=16 {timeit(lambda: nr_ldpc_decode.nr_decode_ldpc(llr, 10, 1, 16, 'BF'), 200):.3f} ms, "
+      f"min-sum L=16 {timeit(lambda: nr_ldpc_decode.nr_decode_ldpc(llr, 10, 1, 16, 'min-sum', 0.8, 0.0), 200):.3f} ms")
