@@ -5,7 +5,7 @@
 
 namespace nrldpc {
 
-#define NRLDPC_SPEC_LIST(X) X(1, 384) X(2, 384) X(1, 352) X(2, 352) X(1, 320) X(2, 320) X(1, 288) X(2, 288) X(1, 256) X(2, 256) X(1, 240) X(2, 240) X(1, 224) X(2, 224) X(1, 208) X(2, 208) X(1, 192) X(2, 192) X(1, 176) X(2, 176) X(1, 160) X(2, 160) X(1, 144) X(2, 144) X(1, 128) X(2, 128) X(1, 72) X(2, 72) X(1, 40) X(2, 40) X(1, 120) X(2, 120) X(1, 112) X(2, 112) X(1, 104) X(2, 104) X(1, 96) X(2, 96) X(1, 88) X(2, 88) X(1, 80) X(2, 80) X(1, 64) X(2, 64) X(1, 60) X(2, 60) X(1, 56) X(2, 56) X(1, 52) X(2, 52) X(1, 48) X(2, 48) X(1, 44) X(2, 44) X(1, 36) X(2, 36) X(1, 32) X(2, 32)
+#define NRLDPC_SPEC_LIST(X) X(1, 384) X(2, 384) X(1, 352) X(2, 352) X(1, 320) X(2, 320) X(1, 288) X(2, 288) X(1, 256) X(2, 256) X(1, 240) X(2, 240) X(1, 224) X(2, 224) X(1, 208) X(2, 208) X(1, 192) X(2, 192) X(1, 176) X(2, 176) X(1, 160) X(2, 160) X(1, 144) X(2, 144) X(1, 128) X(2, 128) X(1, 72) X(2, 72) X(1, 40) X(2, 40) X(1, 120) X(2, 120) X(1, 112) X(2, 112) X(1, 104) X(2, 104) X(1, 96) X(2, 96) X(1, 88) X(2, 88) X(1, 80) X(2, 80) X(1, 64) X(2, 64) X(1, 60) X(2, 60) X(1, 56) X(2, 56) X(1, 52) X(2, 52) X(1, 48) X(2, 48) X(1, 44) X(2, 44) X(1, 36) X(2, 36) X(1, 32) X(2, 32) X(1, 28) X(2, 28) X(1, 24) X(1, 30) X(2, 30) X(1, 26) X(1, 22) X(1, 20)
 
 #define NRLDPC_DECLARE(BGN, ZC)                                                                 \
     int launch_decode_spec_##BGN##_##ZC(const DecArgs &a, int early_term, cudaStream_t s);      \

@@ -124,7 +124,11 @@ template <int BGN, int ZC_, bool RR_ = false> struct Code {
     static constexpr bool RR = RR_;
     // Any lifting size >= 64: r-tile 0 must be full (it writes the 32 mirrored elements).  In a partial last
     // tile the lanes beyond Zc duplicate lane Zc-1 (same loads, same stores of the same values).
-    static_assert(iLS >= 0 && ZC_ >= 32, "specialised kernels need a lifting size >= 32 (a full first r-tile)");
+    // (below 32 the single r-tile is partly filled: its lanes beyond Zc duplicate lane Zc-1, and the 32 mirrored elements
+    // still cover every rotated read, r + P <= 2 Zc - 2 < Zc + 32.  Measured against the table-driven kernel, which packs
+    // several codeblocks into a warp there: BG1 Zc = 20 ... 30 1.24-1.43x, Zc = 18 1.07x, Zc = 16 0.59x; BG2 1.0-1.09x at
+    // Zc = 20 ... 30 -- so BG1 is instantiated from 20 up, BG2 from 28 up)
+    static_assert(iLS >= 0 && ZC_ >= 20, "specialised kernels are instantiated for lifting sizes >= 20");
     static constexpr int nrows = G::rows, kb = G::kb, ncore = G::kb + 4, nnz = G::nnz;
     static constexpr int K = kb * ZC, N = (G::cols - 2) * ZC, Nfull = G::cols * ZC;
     static constexpr int tiles = (ZC + 31) / 32;
