@@ -488,3 +488,67 @@ def test_dlsch_decode_without_soft_buffer(eng, sch_golden):
         assert st2 == st and np.array_equal(tb2, tb) and new2.size == 0 and new.size > 0
         n += 1
     assert n >= 2
+
+
+@pytest.mark.gpu
+def test_fused_sch_chain_fuzz(eng, oracle):
+    """Random transport-block layouts through the fused entry points against the staged chain (oracle rate matching /
+    recovery / combining, the fp32 decoder on the rounded soft buffer): every lifting-size family, Qm, redundancy version,
+    limited buffers that cut into the fillers, heavy repetition, single codeblocks, HARQ combining."""
+    from python_5gtoolbox_b200.ldpc import nr_ldpc_ratematch as RM
+    from tests.conftest import ZLIST
+    rng = np.random.default_rng(20261019)
+    n = 0
+    for trial in range(160):
+        bgn = int(rng.integers(1, 3))
+        Zc = int(rng.choice(ZLIST if trial % 4 else [384, 352, 208, 144, 128, 72, 28, 12]))
+        if Zc > 128 and trial % 4:
+            Zc = int(rng.choice([z for z in ZLIST if z <= 128]))   # keep most trials small
+        C = int(rng.integers(1, 6))
+        Qm = int(rng.choice([1, 2, 4, 6, 8]))
+        NL = int(rng.integers(1, 3))
+        rv = int(rng.integers(0, 4))
+        K, N = ((22, 66) if bgn == 1 else (10, 50))
+        K, N = K * Zc, N * Zc
+        Lcb = 24 if C > 1 else 0
+        F = int(rng.integers(0, max(1, min(2 * Zc, K - Lcb - 2 * Zc - 32))))
+        K_apo = K - F
+        cbz = K_apo - Lcb
+        B = C * cbz
+        if B <= 40:
+            continue
+        Ltb = 24 if B - 24 > 3824 else 16
+        A = B - Ltb
+        if (A > 3824) != (Ltb == 24) or A < 1:
+            continue
+        ncb_frac = float(rng.choice([1.0, 1.0, 0.9, 0.6, 0.35]))
+        Ncb = N if ncb_frac == 1.0 else max(int(N * ncb_frac), 4 * Zc)
+        k0 = RM.get_k0(Ncb, bgn, rv, Zc)
+        scale = float(rng.choice([0.3, 0.6, 1.0, 1.7, 3.2]))
+        G = max(1, int(C * N * scale) // (Qm * NL)) * (Qm * NL) + Qm * NL * int(rng.integers(0, C))
+        Er = RM.get_Er_ldpc(G, C, Qm, NL)
+        if min(Er) <= 0 or max(Er) >= 1 << 24:
+            continue
+        t = dict(bgn=bgn, Zc=Zc, C=C, Qm=Qm, K=K, N=N, K_apo=K_apo, cbz=cbz, A=A, Ltb=Ltb, Ncb=Ncb, k0=k0, Er=Er, G=G)
+        trblk, cbs, g, llr = _make_tb(eng, oracle, rng, t, 4.0)
+        # transmit side: TB CRC + segmentation + encoder with the rate matcher in its store
+        assert np.array_equal(eng.sch_segment_host(trblk, C, K), cbs), t
+        assert np.array_equal(eng.sch_encode_host(trblk, C, bgn, Zc, Ncb, k0, Qm, Er), g), t
+        # receive side, first transmission then one combination
+        off = np.concatenate([[0], np.cumsum(Er)])
+        cur = None
+        for tx in range(2):
+            x = llr if tx == 0 else (llr * rng.uniform(0.5, 1.5)).astype(np.float64)
+            want = np.stack([oracle.raterecover_ldpc(np.asarray(x[off[c]:off[c + 1]], np.float64), Ncb, N, k0, Qm, Zc, K_apo, K) for c in range(C)])
+            if cur is not None:
+                want = oracle.harq_combine(want, cur)
+            r = eng.sch_decode_host(x, Er, bgn, Zc, Ncb, k0, Qm, K_apo, A, 8, 0.75, 0.0, cur=cur)
+            assert np.array_equal(r["soft"], want), (t, tx)
+            d = eng.decode_batch(want.astype(np.float32), Zc, bgn, 8, 0.75, 0.0, True)
+            assert np.array_equal(r["status"], d["status"]) and np.array_equal(r["iters"], d["iters"]), (t, tx)
+            tb = d["ck"][:, :cbz].reshape(-1)
+            assert np.array_equal(r["tbblk"], tb[:A]), (t, tx)
+            assert r["tb_err"] == oracle.crc_decode(tb, '24A' if Ltb == 24 else '16')[1], (t, tx)
+            cur = np.array(want)
+        n += 1
+    assert n >= 100
