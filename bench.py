@@ -424,6 +424,15 @@ def other_kernel_lines(torch, engine, dev, hbm_peak):
                     "bytes_int8_api": api, "gb_per_s_int8_api": api / ms / 1e6, "frac_hbm_int8_api": api / ms / 1e6 / hbm_peak,
                     "bytes_packed_8d": packed, "gb_per_s_packed_8d": packed / ms / 1e6, "frac_hbm_packed_8d": packed / ms / 1e6 / hbm_peak})
         del ck
+    # the bit-packed encoder: what moves IS SURVEY 8(d)'s K/8 + N/8 bytes per codeblock (batch > L2: 1 << 18 codeblocks = 1.1 GB)
+    for bgn, Zc, B in [(1, 384, 1 << 18), (2, 384, 1 << 18)]:
+        K, N, Nf, M = engine.dims(bgn, Zc)
+        ckw = engine.random_bits_packed(B, K, seed=11, device=dev)
+        ms = timed(lambda: engine.encode_packed(ckw, bgn, Zc))
+        packed = B * (K + N) // 8
+        out.append({"kernel": f"encode_packed BG{bgn} Zc={Zc}", "codeblocks": B, "ms": ms, "info_tbit_per_s": B * K / ms / 1e9,
+                    "bytes_packed_8d": packed, "gb_per_s_packed_8d": packed / ms / 1e6, "frac_hbm_packed_8d": packed / ms / 1e6 / hbm_peak})
+        del ckw
     bgn, Zc, B, L = 1, 384, 1 << 14, 20
     K, N, Nf, M = engine.dims(bgn, Zc)
     ck = engine.random_bits(B, K, seed=12, device=dev)

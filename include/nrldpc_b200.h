@@ -61,6 +61,14 @@ int nrldpc_build_csr(int bgn, int Zc, int32_t *rowptr, int32_t *colidx);
  */
 int nrldpc_encode(int8_t *d_ck, int B, int bgn, int Zc, int fix_fillers, int8_t *d_dn, void *stream);
 int nrldpc_encode_host(int8_t *ck, int B, int bgn, int Zc, int fix_fillers, int8_t *dn);
+/*
+ * The same encoder on bit-packed codeblocks -- SURVEY 8(d)'s algorithmic K/8 + N/8 bytes per codeblock instead of the
+ * reference's byte per bit (nr_ldpc_encode.py:8-50 without the filler handling of :32-37: a packed bit cannot be -1).
+ *   ck_words [B, K/32] uint32, bit k of a codeblock at word k / 32, bit k % 32 (the layout of info_packed below);
+ *   dn_words [B, N/32] uint32, same layout.  Zc must be a multiple of 32 (NRLDPC_EINVAL otherwise).
+ * Used by the device-resident Monte-Carlo chain (bits -> CRC -> encode -> AWGN never leave the GPU).
+ */
+int nrldpc_encode_packed(const uint32_t *d_ck_words, int B, int bgn, int Zc, uint32_t *d_dn_words, void *stream);
 
 /* ------------------------------------------------------------------ min-sum decoder (hot path) */
 /*
@@ -180,6 +188,25 @@ int nrldpc_random_bits(int8_t *d_bits, long long count, unsigned long long seed,
  */
 int nrldpc_count_errors(const int8_t *d_ref, long long ref_stride, const int8_t *d_got, long long got_stride,
                         int B, int K, const int32_t *d_iters, long long *d_counters, void *stream);
+
+/*
+ * Bit-packed twins of the four helpers above (word layout of nrldpc_encode_packed; row j of a [rows, row_words] array
+ * starts at word j * row_words, row_words >= ceil(cols / 32), the bits beyond `cols` are written as 0).  Same Philox
+ * counters, so bit k of a row / the noise on it are those of the byte-per-bit functions for the same (seed, id):
+ *   random_bits_packed_rows   cols random bits per row;
+ *   crc_attach_packed         the CRC of the first A bits of every row stored at bits A .. A+L-1, in place
+ *                             (crc.nr_crc_encode, py5gphy/crc/crc.py:4-41); returns L;
+ *   awgn_llr_packed_rows      llr [rows, cols] float32 from packed dn (no fillers);
+ *   count_errors_packed       counters as nrldpc_count_errors, ref and got packed (got = info_packed of the decoder).
+ */
+int nrldpc_random_bits_packed_rows(uint32_t *d_words, long long rows, long long cols, long long row_words,
+                                   unsigned long long seed, long long first_id, long long id_stride, void *stream);
+int nrldpc_crc_attach_packed(uint32_t *d_words, int B, int A, int poly_id, long long row_words, void *stream);
+int nrldpc_awgn_llr_packed_rows(const uint32_t *d_dn_words, long long rows, long long cols, long long row_words, float snr_db,
+                                unsigned long long seed, long long first_id, long long id_stride, float *d_llr, void *stream);
+int nrldpc_count_errors_packed(const uint32_t *d_ref_words, long long ref_row_words, const uint32_t *d_got_words,
+                               long long got_row_words, int B, int K, const int32_t *d_iters, long long *d_counters,
+                               void *stream);
 
 /* ------------------------------------------------------------------ CRC (callers' side of the path) */
 /*

@@ -41,6 +41,11 @@ def _declare(L):
         "nrldpc_build_csr": (i, [i, i, p, p]),
         "nrldpc_encode": (i, [p, i, i, i, i, p, p]),
         "nrldpc_encode_host": (i, [p, i, i, i, i, p]),
+        "nrldpc_encode_packed": (i, [p, i, i, i, p, p]),
+        "nrldpc_random_bits_packed_rows": (i, [p, ll, ll, ll, ull, ll, ll, p]),
+        "nrldpc_crc_attach_packed": (i, [p, i, i, i, ll, p]),
+        "nrldpc_awgn_llr_packed_rows": (i, [p, ll, ll, ll, f, ull, ll, ll, p, p]),
+        "nrldpc_count_errors_packed": (i, [p, ll, p, ll, i, i, p, p, p]),
         "nrldpc_decode_minsum": (i, [p, i, i, i, i, f, f, i, p, p, p, p, p]),
         "nrldpc_decode_minsum_host": (i, [p, i, i, i, i, f, f, i, p, p, p, p]),
         "nrldpc_decode_minsum_host_f16": (i, [p, i, i, i, i, f, f, i, p, p, p, p]),

@@ -288,6 +288,14 @@ int nrldpc_encode(int8_t *d_ck, int B, int bgn, int Zc, int fix_fillers, int8_t 
     return launch_encode(*c, d_ck, B, fix_fillers, d_dn, (cudaStream_t)stream);
 }
 
+int nrldpc_encode_packed(const uint32_t *d_ck_words, int B, int bgn, int Zc, uint32_t *d_dn_words, void *stream)
+{
+    const QcCfg *c = get_cfg(bgn, Zc);
+    if (!c) return NRLDPC_EINVAL;
+    if (B < 0 || !d_ck_words || !d_dn_words) { set_error("encode_packed: bad argument"); return NRLDPC_EINVAL; }
+    return launch_encode_packed(*c, d_ck_words, B, d_dn_words, (cudaStream_t)stream);
+}
+
 int nrldpc_encode_host(int8_t *ck, int B, int bgn, int Zc, int fix_fillers, int8_t *dn)
 {
     const QcCfg *c = get_cfg(bgn, Zc);

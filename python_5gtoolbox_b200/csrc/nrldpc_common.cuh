@@ -102,6 +102,8 @@ struct EncRmArgs {
 };
 int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s,
                   const EncRmArgs *rm = nullptr);
+// bit-packed codeblocks in and out (K/32 and N/32 words per codeblock, no fillers), lifting sizes that are a multiple of 32
+int launch_encode_packed(const QcCfg &cfg, const uint32_t *d_ck_words, int B, uint32_t *d_dn_words, cudaStream_t s);
 struct RrArgs;  // nrldpc_raterecover.cuh
 // rr != nullptr: the LLR load is the rate recovery of a transport block (d_llr unused, early_term must be 1)
 int launch_decode_minsum(const QcCfg &cfg, const float *d_llr, int B, int max_iter, float alpha, float beta,

@@ -273,7 +273,10 @@ __device__ __forceinline__ uint32_t rot2d(const uint32_t *v2w, uint32_t d)
     return __funnelshift_r(p[0], p[1], d);
 }
 
-template <bool ODD>   // ODD: Zc = 16 * odd (half-word stores into the doubled arrays)
+// PACKED: ck / dn are bit-packed (nrldpc_encode_packed: K/32 and N/32 little-endian words per codeblock, bit k of a codeblock
+// at word k / 32, bit k % 32 -- SURVEY 8(d)'s K/8 + N/8 algorithmic bytes); the byte <-> bit stages A and D are plain word
+// copies, there are no fillers (a packed bit cannot be -1) and Zc is a multiple of 32.
+template <bool ODD, bool PACKED = false>   // ODD: Zc = 16 * odd (half-word stores into the doubled arrays)
 __global__ void __launch_bounds__(kWThreads)
 encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ ck, int B, int fix_fillers,
                     int8_t *__restrict__ dn)
@@ -309,7 +312,32 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
     __syncthreads();
 
     // A. pack: one thread per 16 input bytes; the CTA's codeblocks are contiguous in ck
-    {
+    if constexpr (PACKED) {
+        const int KW = kb * W, total = g_cnt * KW;
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(ck) + (long long)cb0 * KW;
+        if ((W & 3) == 0) {
+            // four words at a time: they share their column-block (W % 4 == 0), every offset below is a multiple of 4 words
+            for (int idx = 4 * threadIdx.x; idx < total; idx += 4 * kWThreads) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(base + idx);
+                const int g = __umulhi(2u * (uint32_t)idx, a.mKH), u = idx - g * KW;  // kb H = 2 kb W
+                const int j = __umulhi(2u * (uint32_t)u, a.mH);
+                uint32_t *cbw = smem + g * a.slot + u + j * W;  // word u of [kb][W] -> word u + j W of the doubled [kb][2][W]
+                *reinterpret_cast<uint4 *>(cbw) = v;
+                *reinterpret_cast<uint4 *>(cbw + W) = v;
+                if (j >= 2) *reinterpret_cast<uint4 *>(OUT + g * (NH / 2) + u - 2 * W) = v;
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < total; idx += kWThreads) {
+                const uint32_t v = base[idx];
+                const int g = __umulhi(2u * (uint32_t)idx, a.mKH), u = idx - g * KW;
+                const int j = __umulhi(2u * (uint32_t)u, a.mH);
+                uint32_t *cbw = smem + g * a.slot + u + j * W;
+                cbw[0] = v;
+                cbw[W] = v;
+                if (j >= 2) OUT[g * (NH / 2) + u - 2 * W] = v;
+            }
+        }
+    } else {
         const int KH = kb * H, total = g_cnt * KH;
         uint4 *base = reinterpret_cast<uint4 *>(ck + (long long)cb0 * a.K);
         uint16_t *OUT16 = reinterpret_cast<uint16_t *>(OUT);
@@ -354,6 +382,7 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
     if (act) {
         uint32_t acc = 0;
         const int n = a.nsys[part];
+#pragma unroll 4
         for (int e = 0; e < n; ++e) acc ^= rot2d(Dw, a.sys[part][e]);
         store2(cb + oL1 + part * W2, w, acc);
     }
@@ -382,6 +411,7 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
         uint32_t acc = 0;
         uint16_t *o = out16 + (kb + 2 + part) * H;  // row-block 4 + part -> dn column-block kb - 2 + 4 + part
         const int n = a.next[part];
+#pragma unroll 4
         for (int e = 0; e < n; ++e) {
             const uint32_t d = a.ext[part][e];
             acc ^= rot2d(Dw, d);
@@ -404,7 +434,16 @@ encode_words_kernel(const __grid_constant__ EncWordArgs a, int8_t *__restrict__ 
         return;
     }
     // D. unpack dn: one thread per 16 output bytes, contiguous in dn and in OUT for the CTA's codeblocks
-    {
+    if constexpr (PACKED) {
+        const int total = g_cnt * (NH / 2);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(dn) + (long long)cb0 * (NH / 2);
+        if (((NH / 2) & 3) == 0 && ((a.G * a.slot) & 3) == 0) {
+            for (int idx = 4 * threadIdx.x; idx < total; idx += 4 * kWThreads)
+                *reinterpret_cast<uint4 *>(dst + idx) = *reinterpret_cast<const uint4 *>(OUT + idx);
+        } else {
+            for (int idx = threadIdx.x; idx < total; idx += kWThreads) dst[idx] = OUT[idx];
+        }
+    } else {
         const int total = g_cnt * NH, FH = (kb - 2) * H;
         uint4 *dst = reinterpret_cast<uint4 *>(dn + (long long)cb0 * a.N);
         const uint16_t *OUT16 = reinterpret_cast<const uint16_t *>(OUT);
@@ -435,7 +474,8 @@ int find_edge_host(const QcCfg &c, int i, int j)
     return 0;
 }
 
-int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s, const EncRmArgs &rm)
+int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s, const EncRmArgs &rm,
+                        bool packed = false)
 {
     const int Zc = c.Zc, H = Zc / 16, W = (H + 1) / 2, kb = c.kb, nout = c.ncols - 2;
     EncWordArgs a = {};
@@ -486,16 +526,26 @@ int launch_encode_words(const QcCfg &c, int8_t *d_ck, int B, int fix_fillers, in
     if (dev < 64 && !attr_done[dev]) {
         NRLDPC_CUDA(cudaFuncSetAttribute(encode_words_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         NRLDPC_CUDA(cudaFuncSetAttribute(encode_words_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        NRLDPC_CUDA(cudaFuncSetAttribute(encode_words_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         attr_done[dev] = true;
     }
     const int grid = (B + a.G - 1) / a.G;
-    if (H & 1) encode_words_kernel<true><<<grid, kWThreads, smem_bytes, s>>>(a, d_ck, B, fix_fillers, d_dn);
+    if (packed) encode_words_kernel<false, true><<<grid, kWThreads, smem_bytes, s>>>(a, d_ck, B, 0, d_dn);
+    else if (H & 1) encode_words_kernel<true><<<grid, kWThreads, smem_bytes, s>>>(a, d_ck, B, fix_fillers, d_dn);
     else encode_words_kernel<false><<<grid, kWThreads, smem_bytes, s>>>(a, d_ck, B, fix_fillers, d_dn);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
 }
 
 }  // namespace
+
+int launch_encode_packed(const QcCfg &cfg, const uint32_t *d_ck_words, int B, uint32_t *d_dn_words, cudaStream_t s)
+{
+    if (B <= 0) return NRLDPC_OK;
+    if (cfg.Zc % 32 != 0) { set_error("encode_packed: the lifting size must be a multiple of 32"); return NRLDPC_EINVAL; }
+    return launch_encode_words(cfg, reinterpret_cast<int8_t *>(const_cast<uint32_t *>(d_ck_words)), B, 0,
+                               reinterpret_cast<int8_t *>(d_dn_words), s, EncRmArgs{}, true);
+}
 
 int launch_encode(const QcCfg &cfg, int8_t *d_ck, int B, int fix_fillers, int8_t *d_dn, cudaStream_t s, const EncRmArgs *rm_in)
 {

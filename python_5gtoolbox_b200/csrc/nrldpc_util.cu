@@ -71,18 +71,44 @@ __global__ void random_bits_kernel(int8_t *bits, long long rows, long long cols,
     }
 }
 
+// Bit-packed twin: a Philox block IS four packed words (bit i of the block = bit i % 32 of word i / 32, exactly the bit
+// random_bits_kernel stores as a byte).  One thread per group of four words of a row; the words beyond `cols` are zero.
+__global__ void random_bits_packed_kernel(uint32_t *words, long long rows, long long cols, long long row_words,
+                                          unsigned long long seed, long long first_id, long long id_stride)
+{
+    const long long bpr = (cols + 127) / 128, gpr = (row_words + 3) / 4, ngrp = rows * gpr;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ngrp; t += stride) {
+        const long long row = t / gpr, blk = t - row * gpr;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (blk < bpr) {
+            const uint4 x = philox_at(seed, (unsigned long long)((first_id + row * id_stride) * bpr + blk));
+            w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+        }
+        uint32_t *out = words + row * row_words + blk * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long first_bit = blk * 128 + 32 * q, left = cols - first_bit;  // valid bits of this word
+            if (blk * 4 + q < row_words) out[q] = left >= 32 ? w[q] : (left > 0 ? w[q] & ((1u << left) - 1u) : 0u);
+        }
+    }
+}
+
 // A CTA walks whole rows (one long row: stretches of kAwgnStretch Philox blocks), so that the 64-bit counter base and the row
 // pointers are formed once per stretch and everything per Philox block is 32-bit arithmetic.  The counter of block blk of row j
 // is ctr0 + (first_id + j * id_stride) * bpr + blk, whatever the launch geometry.
 constexpr unsigned kAwgnStretch = 8192;
 
-__global__ void __launch_bounds__(256)
-awgn_llr_kernel(const int8_t *__restrict__ dn, long long rows, long long cols, float sigma, float scale,
+// PACKED: dn is bit-packed (`dnw`, row_words words per row, no fillers) instead of one int8 per bit.
+template <bool PACKED>
+__global__ void __launch_bounds__(256, 8)
+awgn_llr_kernel(const int8_t *__restrict__ dn, const uint32_t *__restrict__ dnw, long long row_words, long long rows,
+                long long cols, float sigma, float scale,
                 unsigned long long seed, unsigned long long ctr0, long long first_id, long long id_stride,
                 float *__restrict__ llr)
 {
     const unsigned long long bpr = (unsigned long long)(cols + 3) / 4;  // one Philox block = 4 normals
-    const bool vec4 = (cols % 4 == 0) && (reinterpret_cast<uintptr_t>(dn) % 4 == 0) && (reinterpret_cast<uintptr_t>(llr) % 16 == 0);
+    const bool vec4 = (cols % 4 == 0) && (PACKED || reinterpret_cast<uintptr_t>(dn) % 4 == 0) && (reinterpret_cast<uintptr_t>(llr) % 16 == 0);
     const unsigned long long spr = (bpr + kAwgnStretch - 1) / kAwgnStretch, nstretch = (unsigned long long)rows * spr;
     const uint2 key = make_uint2((uint32_t)(seed ^ 0x9E3779B97F4A7C15ull), (uint32_t)((seed ^ 0x9E3779B97F4A7C15ull) >> 32));
     const float sig_scale = sigma * scale;  // LLR = scale * (en + sigma n) = scale * en + (sigma scale) * n
@@ -90,7 +116,9 @@ awgn_llr_kernel(const int8_t *__restrict__ dn, long long rows, long long cols, f
         const unsigned long long row = spr == 1 ? st : st / spr, s0 = (st - row * spr) * kAwgnStretch;
         const unsigned nb = (unsigned)min((unsigned long long)kAwgnStretch, bpr - s0);
         const unsigned long long cbase = ctr0 + (unsigned long long)(first_id + (long long)row * id_stride) * bpr + s0;
-        const int8_t *d = dn + row * cols + s0 * 4;
+        const int8_t *d = PACKED ? nullptr : dn + row * cols + s0 * 4;
+        const uint32_t *dw = PACKED ? dnw + row * row_words : nullptr;
+        const unsigned p0 = (unsigned)(s0 * 4);  // bit position of the stretch inside the packed row
         float *o = llr + row * cols + s0 * 4;
         const long long left = cols - (long long)s0 * 4;  // values of this row from the stretch on
         for (unsigned b = threadIdx.x; b < nb; b += blockDim.x) {
@@ -108,6 +136,17 @@ awgn_llr_kernel(const int8_t *__restrict__ dn, long long rows, long long cols, f
             const float n[4] = {r0 * c0f, r0 * s0f, r1 * c1f, r1 * s1f};
             if (vec4) {
                 // :252-257  en = 1 - 2 dn ; fn = en + N(0, sigma) ; LLR = 2 fn / sigma^2 ; a -1 filler is sent as LLR 0
+                if constexpr (PACKED) {
+                    const unsigned p = p0 + 4u * b;  // a multiple of 4: the nibble never straddles two words
+                    const uint32_t w = dw[p >> 5] >> (p & 31u);
+                    float4 v;
+                    v.x = __fmaf_rn(sig_scale, n[0], __uint_as_float(__float_as_uint(scale) ^ ((w << 31) & 0x80000000u)));
+                    v.y = __fmaf_rn(sig_scale, n[1], __uint_as_float(__float_as_uint(scale) ^ ((w << 30) & 0x80000000u)));
+                    v.z = __fmaf_rn(sig_scale, n[2], __uint_as_float(__float_as_uint(scale) ^ ((w << 29) & 0x80000000u)));
+                    v.w = __fmaf_rn(sig_scale, n[3], __uint_as_float(__float_as_uint(scale) ^ ((w << 28) & 0x80000000u)));
+                    *reinterpret_cast<float4 *>(o + 4 * b) = v;
+                    continue;
+                }
                 const uint32_t d4 = *reinterpret_cast<const uint32_t *>(d + 4 * b);
                 float4 v;
                 float *vp = &v.x;
@@ -123,7 +162,9 @@ awgn_llr_kernel(const int8_t *__restrict__ dn, long long rows, long long cols, f
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if ((long long)4 * b + i < left) {
-                        const int dv = d[4 * b + i];
+                        int dv;
+                        if constexpr (PACKED) { const unsigned p = p0 + 4u * b + i; dv = (int)((dw[p >> 5] >> (p & 31u)) & 1u); }
+                        else dv = d[4 * b + i];
                         const float en = dv ? -scale : scale;
                         o[4 * b + i] = dv < 0 ? 0.0f : __fmaf_rn(sig_scale, n[i], en);
                     }
@@ -254,6 +295,78 @@ crc_block_kernel(const __grid_constant__ CrcPow pw, const int8_t *__restrict__ i
     }
 }
 
+// Bit-packed twin of count_errors_kernel: K bits per codeblock, ref / got rows of packed words.
+__global__ void count_errors_packed_kernel(const uint32_t *__restrict__ ref, long long ref_stride,
+                                           const uint32_t *__restrict__ got, long long got_stride, int B, int K,
+                                           const int32_t *__restrict__ iters, unsigned long long *__restrict__ counters)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5, nw = (K + 31) / 32;
+    const uint32_t last = (K & 31) ? ((1u << (K & 31)) - 1u) : 0xffffffffu;
+    unsigned long long blk = 0, bit = 0, its = 0, n = 0;
+    for (int b = warp; b < B; b += nwarps) {
+        int diff = 0;
+        for (int w = lane; w < nw; w += 32) {
+            uint32_t x = ref[b * ref_stride + w] ^ got[b * got_stride + w];
+            if (w == nw - 1) x &= last;
+            diff += __popc(x);
+        }
+        diff = __reduce_add_sync(0xffffffffu, diff);
+        if (lane == 0) {
+            ++n; bit += diff; blk += diff != 0;
+            if (iters) its += iters[b];
+        }
+    }
+    if (lane == 0 && n) {
+        atomicAdd(counters + 0, n);
+        atomicAdd(counters + 1, blk);
+        atomicAdd(counters + 2, bit);
+        atomicAdd(counters + 3, its);
+    }
+}
+
+// Bit-packed twin of crc_block_kernel, mode 0, in place: one CTA per row; the row's A payload bits are staged in shared
+// memory as words, every thread runs the remainder register over its chunk of bits, multiplies by x^(bits after the chunk)
+// mod P and the partial remainders are XOR-reduced; thread 0 stores the L CRC bits at bit positions A .. A+L-1 of the row
+// (remainder MSB first, py5gphy/crc/crc.py:34-38).
+template <int T>
+__global__ void __launch_bounds__(T)
+crc_attach_packed_kernel(const __grid_constant__ CrcPow pw, uint32_t *__restrict__ words, long long row_words, int A, int L,
+                         uint32_t poly)
+{
+    extern __shared__ uint32_t s_w[];
+    __shared__ uint32_t s_part[T / 32];
+    const int tid = threadIdx.x, lane = tid & 31, nw = (A + 31) / 32;
+    uint32_t *x = words + (size_t)blockIdx.x * row_words;
+    for (int k = tid; k < nw; k += T) s_w[k] = x[k];
+    __syncthreads();
+    const uint32_t mask = (L == 32) ? 0xffffffffu : ((1u << L) - 1u);
+    const int chunk = (A + T - 1) / T;
+    const int k0 = min(tid * chunk, A), k1 = min(k0 + chunk, A);
+    uint32_t rem = 0;
+    for (int k = k0; k < k1; ++k) {  // chunk(x) * x^L mod P
+        const uint32_t fb = ((rem >> (L - 1)) ^ (s_w[k >> 5] >> (k & 31))) & 1u;
+        rem = (rem << 1) & mask;
+        if (fb) rem ^= poly;
+    }
+    if (rem && k1 < A) rem = gf2_mulmod(rem, pw.p[tid], L, poly, mask);  // times x^(A - k1) mod P
+#pragma unroll
+    for (int o = 16; o; o >>= 1) rem ^= __shfl_xor_sync(0xffffffffu, rem, o);
+    if (lane == 0) s_part[tid >> 5] = rem;
+    __syncthreads();
+    if (tid == 0) {
+        rem = 0;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) rem ^= s_part[w];
+        // CRC bit k (0 = first) = remainder bit L-1-k -> row bit A + k
+        const unsigned long long crc = (unsigned long long)(__brev(rem) >> (32 - L));
+        const int w0 = A >> 5, sh = A & 31;
+        const unsigned long long val = crc << sh, m = (unsigned long long)mask << sh;
+        x[w0] = (x[w0] & ~(uint32_t)m) | (uint32_t)val;
+        if ((uint32_t)(m >> 32)) x[w0 + 1] = (x[w0 + 1] & ~(uint32_t)(m >> 32)) | (uint32_t)(val >> 32);
+    }
+}
+
 }  // namespace
 
 }  // namespace nrldpc
@@ -295,8 +408,8 @@ extern "C" int nrldpc_awgn_llr_rows(const int8_t *d_dn, long long rows, long lon
 {
     if (rows <= 0 || cols <= 0) return NRLDPC_OK;
     const double sigma = pow(10.0, -(double)snr_db / 20.0), np = pow(10.0, -(double)snr_db / 10.0);
-    awgn_llr_kernel<<<awgn_grid(rows, cols), 256, 0, (cudaStream_t)stream>>>(
-        d_dn, rows, cols, (float)sigma, (float)(2.0 / np), seed, 0, first_id, id_stride, d_llr);
+    awgn_llr_kernel<false><<<awgn_grid(rows, cols), 256, 0, (cudaStream_t)stream>>>(
+        d_dn, nullptr, 0, rows, cols, (float)sigma, (float)(2.0 / np), seed, 0, first_id, id_stride, d_llr);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
 }
@@ -306,8 +419,8 @@ extern "C" int nrldpc_awgn_llr(const int8_t *d_dn, long long count, float snr_db
 {
     if (count <= 0) return NRLDPC_OK;
     const double sigma = pow(10.0, -(double)snr_db / 20.0), np = pow(10.0, -(double)snr_db / 10.0);
-    awgn_llr_kernel<<<awgn_grid(1, count), 256, 0, (cudaStream_t)stream>>>(
-        d_dn, 1, count, (float)sigma, (float)(2.0 / np), seed, offset, 0, 0, d_llr);
+    awgn_llr_kernel<false><<<awgn_grid(1, count), 256, 0, (cudaStream_t)stream>>>(
+        d_dn, nullptr, 0, 1, count, (float)sigma, (float)(2.0 / np), seed, offset, 0, 0, d_llr);
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
 }
@@ -319,6 +432,53 @@ extern "C" int nrldpc_count_errors(const int8_t *d_ref, long long ref_stride, co
     const int grid = (B + 7) / 8 > 148 * 8 ? 148 * 8 : (B + 7) / 8;
     count_errors_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_ref, ref_stride, d_got, got_stride, B, K, d_iters,
                                                                reinterpret_cast<unsigned long long *>(d_counters));
+    NRLDPC_CUDA(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_random_bits_packed_rows(uint32_t *d_words, long long rows, long long cols, long long row_words,
+                                              unsigned long long seed, long long first_id, long long id_stride, void *stream)
+{
+    if (rows < 0 || cols < 0 || row_words < (cols + 31) / 32 || (rows > 0 && !d_words)) {
+        set_error("random_bits_packed_rows: bad argument (row_words >= ceil(cols / 32))");
+        return NRLDPC_EINVAL;
+    }
+    if (rows == 0 || row_words == 0) return NRLDPC_OK;
+    random_bits_packed_kernel<<<grid_for(rows * ((row_words + 3) / 4), 16), 256, 0, (cudaStream_t)stream>>>(
+        d_words, rows, cols, row_words, seed, first_id, id_stride);
+    NRLDPC_CUDA(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_awgn_llr_packed_rows(const uint32_t *d_dn_words, long long rows, long long cols, long long row_words,
+                                           float snr_db, unsigned long long seed, long long first_id, long long id_stride,
+                                           float *d_llr, void *stream)
+{
+    if (rows < 0 || cols < 0 || row_words < (cols + 31) / 32 || (rows > 0 && cols > 0 && (!d_dn_words || !d_llr))) {
+        set_error("awgn_llr_packed_rows: bad argument (row_words >= ceil(cols / 32))");
+        return NRLDPC_EINVAL;
+    }
+    if (rows == 0 || cols == 0) return NRLDPC_OK;
+    const double sigma = pow(10.0, -(double)snr_db / 20.0), np = pow(10.0, -(double)snr_db / 10.0);
+    awgn_llr_kernel<true><<<awgn_grid(rows, cols), 256, 0, (cudaStream_t)stream>>>(
+        nullptr, d_dn_words, row_words, rows, cols, (float)sigma, (float)(2.0 / np), seed, 0, first_id, id_stride, d_llr);
+    NRLDPC_CUDA(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_count_errors_packed(const uint32_t *d_ref_words, long long ref_row_words, const uint32_t *d_got_words,
+                                          long long got_row_words, int B, int K, const int32_t *d_iters, long long *d_counters,
+                                          void *stream)
+{
+    const long long nw = ((long long)K + 31) / 32;
+    if (B < 0 || K < 0 || ref_row_words < nw || got_row_words < nw || !d_counters || (B > 0 && (!d_ref_words || !d_got_words))) {
+        set_error("count_errors_packed: bad argument");
+        return NRLDPC_EINVAL;
+    }
+    if (B == 0) return NRLDPC_OK;
+    const int grid = (B + 7) / 8 > 148 * 8 ? 148 * 8 : (B + 7) / 8;
+    count_errors_packed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_ref_words, ref_row_words, d_got_words, got_row_words, B, K,
+                                                                      d_iters, reinterpret_cast<unsigned long long *>(d_counters));
     NRLDPC_CUDA(cudaGetLastError());
     return NRLDPC_OK;
 }
@@ -397,6 +557,31 @@ extern "C" int nrldpc_crc_check(const int8_t *d_in, int B, int A, int poly_id, u
         else crc_block_launch<64>(d_in, B, A, L, poly, 1, nullptr, d_err, (cudaStream_t)stream);
     }
     else crc_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_in, B, A, L, poly, 1, nullptr, d_err);
+    NRLDPC_CUDA(cudaGetLastError());
+    return L;
+}
+
+extern "C" int nrldpc_crc_attach_packed(uint32_t *d_words, int B, int A, int poly_id, long long row_words, void *stream)
+{
+    int L; uint32_t poly;
+    if (int rc = crc_poly(poly_id, &L, &poly)) return rc;
+    if (B < 0 || A < 0 || row_words < ((long long)A + L + 31) / 32 || (B > 0 && !d_words)) {
+        set_error("crc_attach_packed: bad argument (row_words >= ceil((A + L) / 32))");
+        return NRLDPC_EINVAL;
+    }
+    if (B == 0) return L;
+    const size_t smem = (size_t)((A + 31) / 32) * 4;
+    if (smem > 200 * 1024) { set_error("crc_attach_packed: rows of more than 1.6 Mbit are not supported"); return NRLDPC_EINVAL; }
+    CrcPow pw;
+    if (A >= 32768) {
+        crc_pow_table(A, L, poly, kCrcBlockThreads, &pw);
+        if (smem > 48 * 1024)
+            NRLDPC_CUDA(cudaFuncSetAttribute(crc_attach_packed_kernel<kCrcBlockThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        crc_attach_packed_kernel<kCrcBlockThreads><<<B, kCrcBlockThreads, smem, (cudaStream_t)stream>>>(pw, d_words, row_words, A, L, poly);
+    } else {
+        crc_pow_table(A, L, poly, 64, &pw);
+        crc_attach_packed_kernel<64><<<B, 64, smem, (cudaStream_t)stream>>>(pw, d_words, row_words, A, L, poly);
+    }
     NRLDPC_CUDA(cudaGetLastError());
     return L;
 }

@@ -354,6 +354,65 @@ def count_errors(ref, got, K, iters=None, counters=None):
     return counters
 
 
+# ---- bit-packed twins (SURVEY 8(d)'s K/8 + N/8 bytes per codeblock): int32 tensors of little-endian 32-bit words, bit k
+# of a row at word k // 32, bit k % 32 -- the layout of decode_batch(..., want_info=True)["info"]
+
+def random_bits_packed(rows, cols, seed, device, first_id=0, row_words=None):
+    """`cols` Philox bits per row, packed; bit k of row j equals random_bits_rows' byte (same seed and id)."""
+    import torch
+    row_words = (cols + 31) // 32 if row_words is None else int(row_words)
+    out = torch.empty((rows, row_words), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().nrldpc_random_bits_packed_rows(out.data_ptr(), rows, cols, row_words, int(seed), int(first_id), 1,
+                                                             _stream_ptr()), "random_bits_packed_rows")
+    return out
+
+
+def crc_attach_packed(words, A, poly):
+    """crc.nr_crc_encode on packed rows, in place: the CRC of bits 0..A-1 goes to bits A..A+L-1.  Returns L."""
+    poly_id = {"6": 0, "11": 1, "16": 2, "24A": 3, "24B": 4, "24C": 5}[poly]
+    with __import__("torch").cuda.device(words.device):
+        return _lib.check(_lib.lib().nrldpc_crc_attach_packed(words.data_ptr(), words.shape[0], int(A), poly_id, words.stride(0),
+                                                              _stream_ptr()), "crc_attach_packed")
+
+
+def encode_packed(ck_words, bgn, Zc):
+    """encode_ldpc on packed codeblocks [B, K/32] -> [B, N/32] (no fillers, Zc a multiple of 32)."""
+    import torch
+    K, N, _, _ = dims(bgn, Zc)
+    assert ck_words.is_cuda and ck_words.dtype == torch.int32 and ck_words.is_contiguous() and ck_words.shape[1] * 32 == K
+    out = torch.empty((ck_words.shape[0], N // 32), dtype=torch.int32, device=ck_words.device)
+    with torch.cuda.device(ck_words.device):
+        _lib.check(_lib.lib().nrldpc_encode_packed(ck_words.data_ptr(), ck_words.shape[0], bgn, Zc, out.data_ptr(), _stream_ptr()),
+                   "encode_packed")
+    return out
+
+
+def awgn_llr_packed(dn_words, cols, snr_db, seed, first_id=0, out=None):
+    """awgn_llr_rows on packed dn: llr [rows, cols] float32, the same noise as the byte-per-bit function."""
+    import torch
+    rows = dn_words.shape[0]
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.float32, device=dn_words.device)
+    with torch.cuda.device(dn_words.device):
+        _lib.check(_lib.lib().nrldpc_awgn_llr_packed_rows(dn_words.data_ptr(), rows, int(cols), dn_words.stride(0), float(snr_db),
+                                                          int(seed), int(first_id), 1, out.data_ptr(), _stream_ptr()),
+                   "awgn_llr_packed_rows")
+    return out
+
+
+def count_errors_packed(ref_words, got_words, K, iters=None, counters=None):
+    import torch
+    if counters is None:
+        counters = torch.zeros(4, dtype=torch.int64, device=ref_words.device)
+    with torch.cuda.device(ref_words.device):
+        _lib.check(_lib.lib().nrldpc_count_errors_packed(ref_words.data_ptr(), ref_words.stride(0), got_words.data_ptr(),
+                                                         got_words.stride(0), ref_words.shape[0], int(K),
+                                                         iters.data_ptr() if iters is not None else None,
+                                                         counters.data_ptr(), _stream_ptr()), "count_errors_packed")
+    return counters
+
+
 # ------------------------------------------------------------------ rate matching / recovery, HARQ, CRC (callers' side)
 
 def _offsets(E_list):

@@ -249,9 +249,14 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def _device_point_counters(device, Zc, bgn, snr_db, crcpoly, L, alpha, beta, lo, hi, seed, early_term=True, chunk=16384):
+def _device_point_counters(device, Zc, bgn, snr_db, crcpoly, L, alpha, beta, lo, hi, seed, early_term=True, chunk=16384,
+                           packed=None):
     """{codeblocks, block errors, bit errors, iterations} of codeblocks lo..hi-1 of one SNR point, generated
-    (Philox, codeblock id = its index), encoded, decoded and counted on the device."""
+    (Philox, codeblock id = its index), encoded, decoded and counted on the device.
+
+    packed (default: whenever Zc is a multiple of 32): bits, CRC, codeword and decisions stay bit-packed between the
+    kernels (SURVEY 8(d)'s K/8 + N/8 bytes per codeblock instead of a byte per bit); same Philox counters, so the
+    codeblocks, the noise and therefore the counters are those of the byte-per-bit chain."""
     import ctypes
     import torch
     from . import engine, _lib
@@ -261,9 +266,20 @@ def _device_point_counters(device, Zc, bgn, snr_db, crcpoly, L, alpha, beta, lo,
     poly = {"24A": 3, "24B": 4, "16": 2}[crcpoly]
     counters = torch.zeros(4, dtype=torch.int64, device=device)
     L_ = _lib.lib()
+    if packed is None:
+        packed = Zc % 32 == 0
+    assert not packed or Zc % 32 == 0
     with torch.cuda.device(device):
         for i0 in range(lo, hi, chunk):
             mm = min(chunk, hi - i0)
+            if packed:
+                blk = engine.random_bits_packed(mm, A, seed, device, first_id=i0, row_words=K // 32)
+                engine.crc_attach_packed(blk, A, crcpoly)
+                dn = engine.encode_packed(blk, bgn, Zc)
+                llr = engine.awgn_llr_packed(dn, dn.shape[1] * 32, snr_db, seed, first_id=i0)
+                r = engine.decode_batch(llr, Zc, bgn, L, alpha, beta, early_term, want_ck=False, want_info=True)
+                engine.count_errors_packed(blk, r["info"], K, r["iters"], counters)
+                continue
             s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             bits = torch.empty((mm, A), dtype=torch.int8, device=device)
             _lib.check(L_.nrldpc_random_bits_rows(bits.data_ptr(), mm, A, seed, i0, 1, s), "random_bits")

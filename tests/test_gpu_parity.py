@@ -650,3 +650,88 @@ def test_philox_rows_equal_flat_streams(eng):
         assert int(bits.min()) == 0 and int(bits.max()) == 1
         if rows * cols > 1_000_000:
             assert abs(float(bits.float().mean()) - 0.5) < 0.005
+
+
+# ------------------------------------------------------------------ bit-packed twins (SURVEY 8(d) bytes)
+def _unpack_rows(words, nbits):
+    """[B, W] packed little-endian words -> [B, nbits] int8"""
+    w = words.cpu().numpy().view(np.uint32)
+    return np.unpackbits(w.view(np.uint8), axis=1, bitorder="little")[:, :nbits].astype(np.int8)
+
+
+def test_packed_chain_kernels_match_byte_kernels(eng, oracle):
+    """random bits, CRC attach, encoder, AWGN and the error counters on bit-packed rows against their byte-per-bit
+    twins (same Philox counters: identical bits and bit-identical LLRs), the packed encoder against the oracle, for every
+    lifting size that is a multiple of 32 and the three codeblock CRCs."""
+    import ctypes
+    import torch
+    from python_5gtoolbox_b200 import _lib
+    L_ = _lib.lib()
+    dev = torch.device("cuda")
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for bgn in (1, 2):
+        for Zc in (32, 64, 96, 128, 160, 192, 224, 256, 288, 320, 352, 384):
+            K, N, Nf, M = eng.dims(bgn, Zc)
+            for crcpoly, first_id in (("24A", 0), ("24B", 12345), ("16", 7)):
+                B = 37 if Zc < 384 else 300
+                crc_len = 16 if crcpoly == "16" else 24
+                A = K - crc_len
+                poly = {"24A": 3, "24B": 4, "16": 2}[crcpoly]
+                seed = 0x5601 + Zc + bgn
+                # byte chain
+                bits = torch.empty((B, A), dtype=torch.int8, device=dev)
+                _lib.check(L_.nrldpc_random_bits_rows(bits.data_ptr(), B, A, seed, first_id, 1, s))
+                blk = torch.empty((B, K), dtype=torch.int8, device=dev)
+                _lib.check(L_.nrldpc_crc_encode(bits.data_ptr(), B, A, poly, blk.data_ptr(), s))
+                dn = eng.encode_batch(blk, bgn, Zc, fix_fillers=False)
+                llr = torch.empty(dn.shape, dtype=torch.float32, device=dev)
+                _lib.check(L_.nrldpc_awgn_llr_rows(dn.data_ptr(), B, N, 0.5, seed, first_id, 1, llr.data_ptr(), s))
+                # packed chain
+                pw = eng.random_bits_packed(B, A, seed, dev, first_id=first_id, row_words=K // 32)
+                assert np.array_equal(_unpack_rows(pw, K)[:, :A], bits.cpu().numpy()) and not _unpack_rows(pw, K)[:, A:].any()
+                assert eng.crc_attach_packed(pw, A, crcpoly) == crc_len
+                assert np.array_equal(_unpack_rows(pw, K), blk.cpu().numpy()), (bgn, Zc, crcpoly)
+                dw = eng.encode_packed(pw, bgn, Zc)
+                assert np.array_equal(_unpack_rows(dw, N), dn.cpu().numpy()), (bgn, Zc)
+                pl = eng.awgn_llr_packed(dw, N, 0.5, seed, first_id=first_id)
+                assert torch.equal(pl, llr), (bgn, Zc)
+                # counters: packed decisions with a few planted errors against the byte counters
+                got = blk.clone()
+                got[1, 5] ^= 1
+                got[2, K - 1] ^= 1
+                got[2, 0] ^= 1
+                gw = torch.from_numpy(np.packbits(got.cpu().numpy().astype(np.uint8), axis=1, bitorder="little").view(np.int32).copy()).to(dev)
+                it = torch.arange(B, dtype=torch.int32, device=dev)
+                c1 = eng.count_errors(blk, got, K, it)
+                c2 = eng.count_errors_packed(pw, gw, K, it)
+                assert c1.tolist() == c2.tolist() == [B, 2, 3, B * (B - 1) // 2]
+            if Zc in (32, 224, 384):
+                ck = _unpack_rows(pw, K)[:8].copy()
+                assert np.array_equal(_unpack_rows(dw, N)[:8], oracle.encode_batch(ck, bgn, Zc)), (bgn, Zc)
+    # a row stride larger than the payload, a bit count that is not a multiple of 32, and the argument checks
+    pw = eng.random_bits_packed(5, 1000, 99, dev, first_id=3, row_words=40)
+    bits = torch.empty((5, 1000), dtype=torch.int8, device=dev)
+    _lib.check(L_.nrldpc_random_bits_rows(bits.data_ptr(), 5, 1000, 99, 3, 1, s))
+    u = _unpack_rows(pw, 1280)
+    assert np.array_equal(u[:, :1000], bits.cpu().numpy()) and not u[:, 1000:].any()
+    assert eng.crc_attach_packed(pw, 1000, "24A") == 24
+    ref = torch.empty((5, 1024), dtype=torch.int8, device=dev)
+    _lib.check(L_.nrldpc_crc_encode(bits.data_ptr(), 5, 1000, 3, ref.data_ptr(), s))
+    assert np.array_equal(_unpack_rows(pw, 1024), ref.cpu().numpy())
+    with pytest.raises(AssertionError):
+        eng.encode_packed(torch.zeros((2, 22 * 48 // 32), dtype=torch.int32, device=dev), 1, 48)
+    assert L_.nrldpc_crc_attach_packed(pw.data_ptr(), 5, 1270, 3, 40, s) == _lib.EINVAL   # the CRC would not fit in the row
+
+
+def test_packed_monte_carlo_chain_same_counters(eng):
+    """The bit-packed device chain of sim.bler_curve counts exactly what the byte-per-bit chain counts."""
+    import torch
+    from python_5gtoolbox_b200 import sim
+    dev = torch.device("cuda")
+    mixed = 0
+    for Zc, bgn, snr, n in ((64, 1, -0.5, 3000), (384, 1, -0.7, 700), (384, 1, -3.0, 300), (128, 2, -1.0, 2000)):
+        a = sim._device_point_counters(dev, Zc, bgn, snr, "24A", 10, 0.8, 0.0, 100, 100 + n, 0x5601, chunk=512, packed=True)
+        b = sim._device_point_counters(dev, Zc, bgn, snr, "24A", 10, 0.8, 0.0, 100, 100 + n, 0x5601, chunk=1000, packed=False)
+        assert a.tolist() == b.tolist() and a[0] == n and a[2] >= a[1], (Zc, bgn, a.tolist(), b.tolist())
+        mixed += 0 < a[1] < n
+    assert mixed >= 1   # points with both failing and converging codeblocks
