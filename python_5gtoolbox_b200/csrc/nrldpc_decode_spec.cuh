@@ -89,6 +89,9 @@ constexpr int kNoVariant = 1;  // launch_spec: this (early_term) combination is 
 #ifndef NRLDPC_FINAL_PACKED
 #define NRLDPC_FINAL_PACKED 1  // final syndrome on bit-packed hard decisions (lifting sizes that are a multiple of 32)
 #endif
+#ifndef NRLDPC_LLR_OPAQUE
+#define NRLDPC_LLR_OPAQUE 0
+#endif
 #ifndef NRLDPC_PF_SUM
 #define NRLDPC_PF_SUM 20  // prefetch the next check row's inputs when deg(current) + deg(next) <= this (registers)
 #endif
@@ -798,6 +801,9 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
             th.llr = row + th.r;
         } else {
             th.llr = a.llr + (size_t)cb * C::N + th.r;
+#if NRLDPC_LLR_OPAQUE
+            asm volatile("" : "+l"(th.llr));  // keep the row pointer in a register pair (otherwise re-derived from cb and r at every LDG)
+#endif
         }
 #ifndef NRLDPC_EXP_NO_PF
         if (!dyn) {
