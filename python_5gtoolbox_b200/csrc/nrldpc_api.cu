@@ -492,10 +492,21 @@ static int decode_minsum_host_impl(const void *llr, bool f16, int B, int bgn, in
         }
     }
     if (rc != NRLDPC_OK) return fail(rc);
+    // Chunk schedule.  The path is bound by the host link, so what is exposed is the first chunk's copy (nothing to decode
+    // yet) and the last chunk's decode (nothing left to copy): both are kept to one wave of codeblocks (one per SM) when the
+    // batch is large enough, and the chunks in between are whole waves.
+    int sms = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    int edge = 0;  // codeblocks of the first and of the last chunk (0: uniform chunks)
+    if (chunk >= 2 * sms && B >= 4 * chunk) { edge = sms; chunk -= chunk % sms; }
     int k = 0;
-    for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
+    for (int b0 = 0, nb = 0; b0 < B; b0 += nb, ++k) {
         HostStage &S = st[k % nstage];
-        const int nb = std::min(chunk, B - b0);
+        nb = std::min(chunk, B - b0);
+        if (edge) {
+            if (b0 == 0) nb = edge;
+            else if (B - b0 > edge) nb = std::min(chunk, B - b0 - edge);
+        }
         if ((rc = S.drain()) != NRLDPC_OK) return fail(rc);
         if (!f16) {
             if ((rc = h2d_async(S.buf[0], (const float *)llr + (size_t)b0 * c->N, (size_t)nb * llr_bytes, S.s)) != NRLDPC_OK) return fail(rc);

@@ -735,3 +735,25 @@ def test_packed_monte_carlo_chain_same_counters(eng):
         assert a.tolist() == b.tolist() and a[0] == n and a[2] >= a[1], (Zc, bgn, a.tolist(), b.tolist())
         mixed += 0 < a[1] < n
     assert mixed >= 1   # points with both failing and converging codeblocks
+
+
+def test_host_pipeline_graded_chunks_equal_device_path(eng):
+    """nrldpc_decode_minsum_host on a batch large enough for the graded chunk schedule (one wave first, whole waves in
+    between, one wave last): every codeblock decoded exactly once, in order -- results equal to the device entry point's,
+    from pinned and from pageable memory, with and without early termination."""
+    import torch
+    bgn, Zc, B = 1, 384, 1500   # 32 MiB chunks = 331 -> 296 codeblocks; B >= 4 chunks
+    K, N, Nf, M = eng.dims(bgn, Zc)
+    ck = eng.random_bits(B, K, seed=5, device="cuda")
+    llr = eng.awgn_llr(eng.encode_batch(ck, bgn, Zc), -0.6, seed=6)
+    host = llr.cpu().numpy()
+    pinned = eng.pinned_empty(host.shape, np.float32)
+    pinned[...] = host
+    for et in (True, False):
+        d = eng.decode_batch(llr, Zc, bgn, 10, 0.8, 0.0, et, want_ck=True, want_info=True)
+        for src in (host, pinned):
+            h = eng.decode_batch(src, Zc, bgn, 10, 0.8, 0.0, et, want_ck=True, want_info=True)
+            assert np.array_equal(h["iters"], d["iters"].cpu().numpy()) and np.array_equal(h["status"], d["status"].cpu().numpy().astype(bool))
+            assert np.array_equal(h["ck"], d["ck"].cpu().numpy())
+            assert np.array_equal(h["info"], d["info"].cpu().numpy().view(np.uint32))
+    assert len(np.unique(ck.cpu().numpy()[:, :64], axis=0)) == B   # the codeblocks are distinguishable: order is checked too
