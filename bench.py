@@ -569,10 +569,10 @@ def ctypes_int():
 
 # Cited, not measured by this run: the committed `ncu --set full` capture of the same kernel, profiles/prof_r2_decode.ncu-rep
 # (592 codeblocks; raw page profiles/prof_r2_decode_raw.csv, summary profiles/r2_ncu_summary.md):
-#   dram__bytes_read.sum + dram__bytes_write.sum = 60 183 808 B + 389 376 B;  smsp__inst_executed.sum = 466 189 936
+#   dram__bytes_read.sum + dram__bytes_write.sum = 60 185 088 B + 399 616 B;  smsp__inst_executed.sum = 469 770 352
 NCU_CAPTURE = "profiles/prof_r2_decode.ncu-rep"
-TRAFFIC_BYTES_PER_CB = (60183808 + 389376) / 592
-WARP_INSTR_PER_CB = 466189936 / 592
+TRAFFIC_BYTES_PER_CB = (60185088 + 399616) / 592
+WARP_INSTR_PER_CB = 469770352 / 592
 
 
 def main():

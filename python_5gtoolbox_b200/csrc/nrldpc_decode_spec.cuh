@@ -89,6 +89,12 @@ constexpr int kNoVariant = 1;  // launch_spec: this (early_term) combination is 
 #ifndef NRLDPC_FINAL_PACKED
 #define NRLDPC_FINAL_PACKED 1  // final syndrome on bit-packed hard decisions (lifting sizes that are a multiple of 32)
 #endif
+#ifndef NRLDPC_XSIGN
+#define NRLDPC_XSIGN 1   // 1: rows of odd degree apply the old message's sign to the posterior instead of the magnitude
+#endif                   // (Lq' = s Lq = s x - |Lr|: two predicated FADDs choose the magnitude, no FSEL; see cn_edge_s)
+#ifndef NRLDPC_XSIGN_MIN_ZC
+#define NRLDPC_XSIGN_MIN_ZC 288  // measured: +1.0-1.6 % at Zc = 288 ... 384 (24-30 warps, ALU-pipe bound), -0.5 ... -3 % at 144 ... 256
+#endif
 #ifndef NRLDPC_LLR_OPAQUE
 #define NRLDPC_LLR_OPAQUE 0
 #endif
@@ -250,6 +256,19 @@ template <class C, int I, int K> __device__ __forceinline__ bool is_argmin(const
 #endif
 }
 
+// y - (edge K is the argmin edge of the row ? m.y : m.x): the magnitude is chosen by predicating two FADDs on the argmin test
+// (FMA pipe) instead of an FSEL on the ALU pipe, which bounds the check pass.
+template <class C, int I, int K> __device__ __forceinline__ float sub_record_mag(const Th<C> &th, float y, float2 m, uint32_t bits)
+{
+    float q = __fsub_rn(y, m.x);
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+        "lop3.b32 t, %3, %4, %5, 0x28;\n\t"
+        "setp.eq.b32 p, t, 0;\n\t"
+        "@p sub.rn.f32 %0, %1, %2;\n\t}"
+        : "+f"(q) : "f"(y), "f"(m.y), "r"(bits), "r"((uint32_t)K << C::idx_shift(I)), "r"(th.mk[C::kind(I)]));
+    return q;
+}
+
 // sign/argmin word access
 template <class C, int I> __device__ __forceinline__ uint32_t load_bits(const char *p)
 {
@@ -311,6 +330,13 @@ template <class C, int I, bool FIRST = false> __device__ __forceinline__ RowIn<C
     return in;
 }
 
+// Rows handled with the sign on the posterior (NRLDPC_XSIGN): odd degree only -- the parity of a stored sign word is
+// XOR_k (sp ^ sign Lq_k) = (DEG + 1) sp, i.e. 0 for an odd degree, so XOR_k s_k needs no instruction there.
+template <class C, int I, bool FIRST> __device__ __forceinline__ constexpr bool xsign_row()
+{
+    return NRLDPC_XSIGN && C::ZC >= NRLDPC_XSIGN_MIN_ZC && !FIRST && (C::deg(I) % 2 == 1);
+}
+
 template <class C, int I, int K, bool ET, bool FIRST>
 __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, float &m2, uint32_t &synd, const Th<C> &th,
                                           const RowIn<C, I> &in, uint32_t idxf, float llr_e)
@@ -318,6 +344,43 @@ __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, floa
     constexpr int DEG = C::deg(I);
     constexpr bool EXT = I >= 4;
     float lr = 0.f;  // FIRST: Lr = +0 on every edge
+    if constexpr (xsign_row<C, I, FIRST>()) {
+        // Lq' = s Lq with s = the sign of the old message: s x - |Lr| = s (x - s |Lr|) exactly, so |Lq'| = |Lq| and
+        // sign(Lq) = s ^ sign(Lq') (a zero Lq' gets the sign s: the sign given to a zero cancels in every message, see
+        // cn_row_s).  The row's sign product and sign word are corrected once per row.
+        const uint32_t sbit = (in.bits << (31 - (DEG - 1 - K))) & 0x80000000u;
+        float x;
+        if constexpr (EXT && K == DEG - 1 && !ET) {
+            // s x = s LLR + |Lr| and Lq' = s x - |Lr|: both magnitudes by predicated FADDs (x itself is not needed)
+            const float t = __uint_as_float(__float_as_uint(llr_e) ^ sbit);
+            x = 0.f;
+            const float y = sub_record_mag<C, I, K>(th, t, make_float2(-in.m.x, -in.m.y), in.bits);
+            q[K] = sub_record_mag<C, I, K>(th, y, in.m, in.bits);
+        } else if constexpr (EXT && K == DEG - 1) {
+            const bool isidx = is_argmin<C, I, K>(th, in.bits);
+            const float mag = isidx ? in.m.y : in.m.x;
+            x = __fadd_rn(llr_e, __uint_as_float(__float_as_uint(mag) ^ sbit));  // posterior of the extension variable (:126)
+            if constexpr (ET) {
+                const uint32_t hb = __ballot_sync(0xffffffffu, x < 0.f);
+                if ((th.r & 31) == 0) reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + th.tile] = hb;
+            }
+            q[K] = __fsub_rn(__uint_as_float(__float_as_uint(x) ^ sbit), mag);
+        } else {
+            x = in.x[K];
+            q[K] = sub_record_mag<C, I, K>(th, __uint_as_float(__float_as_uint(x) ^ sbit), in.m, in.bits);
+        }
+        if constexpr (ET) synd ^= __float_as_uint(x);
+        if constexpr (K == 0) {
+            m1 = q[0];
+        } else if constexpr (K == 1) {
+            m2 = fmaxf(fabsf(m1), fabsf(q[1]));
+            m1 = min_xorsign_abs(m1, q[1]);
+        } else {
+            m2 = fminf(m2, fmaxf(fabsf(m1), fabsf(q[K])));
+            m1 = min_xorsign_abs(m1, q[K]);
+        }
+        return;
+    }
     if constexpr (!FIRST) {
 #if NRLDPC_MASKREG
         const bool isidx = is_argmin<C, I, K>(th, in.bits);
@@ -426,7 +489,9 @@ __device__ __forceinline__ void cn_row_s(const DecArgs &a, const Th<C> &th, int 
     const float mag1 = B0 ? __fmul_rn(a.alpha, fabsf(m1)) : __fmul_rn(a.alpha, fmaxf(__fsub_rn(fabsf(m1), a.beta), 0.f));
     const float mag2 = B0 ? __fmul_rn(a.alpha, m2) : __fmul_rn(a.alpha, fmaxf(__fsub_rn(m2, a.beta), 0.f));
     const uint32_t sp = (uint32_t)((int)__float_as_uint(m1) >> 31);  // all ones when the sign product is -
-    const uint32_t nb = ((sacc ^ sp) & ALL) | ((kmin << C::idx_shift(I)) & C::idx_mask(I));
+    // (sign on the posterior: sacc holds sign(Lq') = s ^ sign(Lq), and XOR_k s_k = 0, so the row's sign product is sp as it is)
+    const uint32_t nb = (xsign_row<C, I, FIRST>() ? ((sacc ^ in.bits ^ sp) & ALL) : ((sacc ^ sp) & ALL))
+                      | ((kmin << C::idx_shift(I)) & C::idx_mask(I));
     *reinterpret_cast<float *>(rec) = mag1;
     *reinterpret_cast<float *>(rec + C::mag2_dist) = mag2;
     store_bits<C, I>(bp, nb);
