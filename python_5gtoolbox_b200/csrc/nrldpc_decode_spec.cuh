@@ -233,6 +233,18 @@ template <class C> constexpr Deal deal_cols()
 template <class C> inline constexpr Deal kRows = deal_rows<C>();
 template <class C> inline constexpr Deal kCols = deal_cols<C>();
 
+// Final syndrome on bit-packed hard decisions (below): lifting sizes that are a multiple of 32 whose packed words fit in the
+// dead records of row-blocks 0-3.
+template <class C> constexpr bool kFinalPacked = NRLDPC_FINAL_PACKED && C::ZC % 32 == 0 && 2 * C::tiles * C::ncore * 4 <= 4 * C::LQS * 4;
+// Early termination: do the check passes store the hard bits of the extension variables every iteration?  Only where they cannot
+// be derived at the exit: a codeblock leaves with every parity check satisfied, so the bit of a row-block's degree-1 extension
+// variable IS the XOR of its core bits -- one pass over the packed core decisions at the exit (ext_from_core), and only when the
+// caller wants ck at all, instead of FSETP + VOTE + predicated STS per extension row and iteration on the ALU-bound check pass.
+#ifndef NRLDPC_ET_EXT_AT_EXIT
+#define NRLDPC_ET_EXT_AT_EXIT 1
+#endif
+template <class C> constexpr bool kEtStoresExt = !(NRLDPC_ET_EXT_AT_EXIT && kFinalPacked<C>);
+
 template <class C> struct Th {  // per-thread constants
     char *smem;                 // the CTA's codeblock state
     const float *llr;           // this thread's codeblock LLR row, already offset by r
@@ -360,7 +372,7 @@ __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, floa
             const bool isidx = is_argmin<C, I, K>(th, in.bits);
             const float mag = isidx ? in.m.y : in.m.x;
             x = __fadd_rn(llr_e, __uint_as_float(__float_as_uint(mag) ^ sbit));  // posterior of the extension variable (:126)
-            if constexpr (ET) {
+            if constexpr (ET && kEtStoresExt<C>) {
                 const uint32_t hb = __ballot_sync(0xffffffffu, x < 0.f);
                 if ((th.r & 31) == 0) reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + th.tile] = hb;
             }
@@ -392,7 +404,7 @@ __device__ __forceinline__ void cn_edge_s(float (&q)[C::deg(I)], float &m1, floa
     float x;
     if constexpr (EXT && K == DEG - 1) {
         x = __fadd_rn(llr_e, lr);  // posterior of the degree-1 extension variable (:126); -0.0 + 0 = +0.0
-        if constexpr (ET) {
+        if constexpr (ET && kEtStoresExt<C>) {
             const uint32_t hb = __ballot_sync(0xffffffffu, x < 0.f);
             if ((th.r & 31) == 0) reinterpret_cast<uint32_t *>(th.smem + C::off_ext)[(I - 4) * C::tiles + th.tile] = hb;
         }
@@ -714,15 +726,15 @@ template <class C> constexpr FinalTab<C> make_final_tab()
 }
 template <class C> __constant__ FinalTab<C> kFinalTab = make_final_tab<C>();
 
-template <class C> constexpr bool kFinalPacked = NRLDPC_FINAL_PACKED && C::ZC % 32 == 0 && 2 * C::tiles * C::ncore * 4 <= 4 * C::LQS * 4;
 
 // step 1 (all warps, after the last variable pass): pack the hard decisions of this warp group's columns
-template <class C> __device__ __forceinline__ void final_pack(int sub, const Th<C> &th, uint32_t *hbw)
+// (LT: the in-loop tie rule LQ < 0 -> 1 of a codeblock that leaves early, :107-108, instead of the final LQ <= 0 -> 1)
+template <class C, bool LT = false> __device__ __forceinline__ void final_pack(int sub, const Th<C> &th, uint32_t *hbw)
 {
     const int lane = th.r & 31;
     for (int j = sub; j < C::ncore; j += C::S) {
         const float x = *reinterpret_cast<const float *>(th.smem + C::lq_base(j) + th.r4);
-        const uint32_t word = __ballot_sync(0xffffffffu, x <= 0.f);
+        const uint32_t word = __ballot_sync(0xffffffffu, LT ? (x < 0.f) : (x <= 0.f));
         if (lane == 0) hbw[j * 2 * C::tiles + th.tile] = hbw[j * 2 * C::tiles + C::tiles + th.tile] = word;
     }
 }
@@ -740,6 +752,25 @@ template <class C> __device__ __forceinline__ void final_syndrome(int warp, int 
                 acc ^= __funnelshift_r(v[0], v[1], t >> 9);
             }
             if (acc) flag[0] = 1;
+        }
+    }
+}
+
+// Early exit with all parity checks satisfied: hard-bit word w of the extension variable of row-block i = XOR over the row-block's
+// core edges of the rotated core words (same walk as final_syndrome); warp `warp` takes row-blocks 4 + warp, 4 + warp + nwarps, ...
+template <class C> __device__ __forceinline__ void ext_from_core(int warp, int lane, const uint32_t *hbw, uint32_t *ext)
+{
+    for (int i = 4 + warp; i < C::nrows; i += C::nwarps) {
+        const int e0 = kFinalTab<C>.start[i], e1 = kFinalTab<C>.start[i + 1];
+        if (lane < C::tiles) {
+            uint32_t acc = 0u;
+#pragma unroll 4
+            for (int e = e0; e < e1; ++e) {
+                const uint32_t t = kFinalTab<C>.e[e];
+                const uint32_t *v = hbw + (t & 31u) * (2 * C::tiles) + ((t >> 5) & 15u) + lane;
+                acc ^= __funnelshift_r(v[0], v[1], t >> 9);
+            }
+            ext[(i - 4) * C::tiles + lane] = acc;
         }
     }
 }
@@ -953,6 +984,15 @@ decode_spec_kernel(const __grid_constant__ DecArgs a)
             if (a.iters) a.iters[cb] = it;
         }
         const uint32_t *ext = reinterpret_cast<const uint32_t *>(smem + C::off_ext);
+        if constexpr (ET && !kEtStoresExt<C>) {
+            if (et_done && a.ck) {  // (block-uniform) the extension bits of a converged codeblock, from its core decisions
+                uint32_t *hbw = reinterpret_cast<uint32_t *>(smem + C::mags_base(0));  // the records are dead
+                final_pack<C, true>(sub, th, hbw);
+                __syncthreads();
+                ext_from_core<C>(warp, lane, hbw, reinterpret_cast<uint32_t *>(smem + C::off_ext));
+                __syncthreads();
+            }
+        }
         if (a.ck) {
             int8_t *out = a.ck + (size_t)cb * C::Nfull;
             for (int j = 0; j < C::ncore; ++j) {
