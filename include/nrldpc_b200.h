@@ -65,7 +65,7 @@ int nrldpc_encode_host(int8_t *ck, int B, int bgn, int Zc, int fix_fillers, int8
  * The same encoder on bit-packed codeblocks -- SURVEY 8(d)'s algorithmic K/8 + N/8 bytes per codeblock instead of the
  * reference's byte per bit (nr_ldpc_encode.py:8-50 without the filler handling of :32-37: a packed bit cannot be -1).
  *   ck_words [B, K/32] uint32, bit k of a codeblock at word k / 32, bit k % 32 (the layout of info_packed below);
- *   dn_words [B, N/32] uint32, same layout.  Zc must be a multiple of 32 (NRLDPC_EINVAL otherwise).
+ *   dn_words [B, N/32] uint32, same layout.  Zc must be a multiple of 32 and both arrays 16-byte aligned (NRLDPC_EINVAL otherwise).
  * Used by the device-resident Monte-Carlo chain (bits -> CRC -> encode -> AWGN never leave the GPU).
  */
 int nrldpc_encode_packed(const uint32_t *d_ck_words, int B, int bgn, int Zc, uint32_t *d_dn_words, void *stream);

@@ -543,6 +543,10 @@ int launch_encode_packed(const QcCfg &cfg, const uint32_t *d_ck_words, int B, ui
 {
     if (B <= 0) return NRLDPC_OK;
     if (cfg.Zc % 32 != 0) { set_error("encode_packed: the lifting size must be a multiple of 32"); return NRLDPC_EINVAL; }
+    if ((reinterpret_cast<uintptr_t>(d_ck_words) | reinterpret_cast<uintptr_t>(d_dn_words)) % 16 != 0) {
+        set_error("encode_packed: ck_words and dn_words must be 16-byte aligned (128-bit word copies)");
+        return NRLDPC_EINVAL;
+    }
     return launch_encode_words(cfg, reinterpret_cast<int8_t *>(const_cast<uint32_t *>(d_ck_words)), B, 0,
                                reinterpret_cast<int8_t *>(d_dn_words), s, EncRmArgs{}, true);
 }

@@ -721,6 +721,9 @@ def test_packed_chain_kernels_match_byte_kernels(eng, oracle):
     with pytest.raises(AssertionError):
         eng.encode_packed(torch.zeros((2, 22 * 48 // 32), dtype=torch.int32, device=dev), 1, 48)
     assert L_.nrldpc_crc_attach_packed(pw.data_ptr(), 5, 1270, 3, 40, s) == _lib.EINVAL   # the CRC would not fit in the row
+    w = torch.zeros((2, 22 * 32 // 32 + 1), dtype=torch.int32, device=dev)
+    o = torch.zeros((2, 66), dtype=torch.int32, device=dev)
+    assert L_.nrldpc_encode_packed(w.data_ptr() + 4, 1, 1, 32, o.data_ptr(), s) == _lib.EINVAL   # misaligned input words
 
 
 def test_packed_monte_carlo_chain_same_counters(eng):
