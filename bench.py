@@ -365,7 +365,7 @@ def run_ours(args):
                                   "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": per_gpu_cbs * WARP_INSTR_PER_CB / issue_peak,
                                   "warp_instr_per_codeblock": WARP_INSTR_PER_CB,
                                   "source": f"smsp__inst_executed.sum of {NCU_CAPTURE} / 592 codeblocks (cited, not measured by this run); "
-                                            "ALU pipe 68 %, issue 78 %, smem wavefronts 62 % busy in that capture"}
+                                            "ALU pipe 65 %, issue 80 %, smem wavefronts 63 % busy in that capture"}
         if not args.no_cpu and world == 1:   # reported at N=1 only (rank 0); ~10 s of CPU work on all host cores
             ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             gbps, threads, n, sps = cpu_reference_run(1, 0, sample_cbs=max(400 * ncores, 256))
