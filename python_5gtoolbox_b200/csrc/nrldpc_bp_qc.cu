@@ -2,9 +2,9 @@
 //
 // Replaces nr_decode_ldpc(..., algo='BP') = decode_ldpc + _BP_process (py5gphy/ldpc/nr_ldpc_decode.py:51-143, :145-176)
 // for the 5G matrices, which before went through the generic CSR kernel with a host round trip per batch.  Same flooding
-// schedule and operation order as the reference, float64 arithmetic like the reference (tanh / atanh are the device
-// libm's, so intermediate LLRs are not bit-identical to NumPy's; hard decisions, status and iteration counts are what
-// the goldens pin):
+// schedule and operation order as the reference, float64 arithmetic like the reference (tanh / atanh are this library's
+// own, nrldpc_bp_math.cuh, within 3 ulp: intermediate LLRs are not bit-identical to NumPy's, as with any other libm; hard
+// decisions, status and iteration counts are what the goldens pin):
 //   per row:  t_e = tanh(Lq_e / 2), P = prod t_e, Lr_e = 2 atanh(P / t_e) clipped to +-38.14 when |x| >= 1 (:158-163);
 //             exactly one zero input: that edge gets prod tanh(others) WITHOUT the 2 atanh (:164-170); >= 2 zeros: 0.
 // Per-edge messages are needed (no min1/min2 compression for BP): Lr[nnz][Zc] doubles = 970 KB per codeblock at BG1
@@ -13,12 +13,14 @@
 // index arithmetic on the lifted index, the tables sit in the constant bank (QcCfg by value).
 #include <algorithm>
 
+#include "nrldpc_bp_math.cuh"
 #include "nrldpc_common.cuh"
 
 namespace nrldpc {
 namespace {
 
 constexpr int kBpThreads = 512;
+constexpr int kBpBatch = 4;  // edges of a row whose workspace words are in flight together
 
 template <typename TIn>
 __global__ void __launch_bounds__(kBpThreads)
@@ -76,31 +78,59 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
             if (tid == 0) s_any = 0;
             if (!bad && early_term) { done = true; break; }
 
-            // :117-123 every check row from the old Lq = LQ - Lr; pass 1 leaves tanh(Lq/2) in the message slot
+            // :117-123 every check row from the old Lq = LQ - Lr; sweep 1 leaves tanh(Lq/2) in the message slot.
+            // Both sweeps request the workspace words of kBpBatch edges before they start on the arithmetic (the loads are
+            // L2 / HBM latency); the degree-1 extension edge of rows >= 4 (the row's last edge) is handled on its own.
             for (int m = tid; m < nchk; m += kBpThreads) {
                 const int i = m / Zc, r = m - i * Zc;
-                const int e0 = c.rowptr[i], e1 = c.rowptr[i + 1];
+                const int e0 = c.rowptr[i], ne = c.rowptr[i + 1] - e0, nce = ne - (i >= 4);
+                double *slot0 = Lr + (size_t)e0 * Zc + r;  // edge k of the row: slot0[k * Zc]
                 int nz = 0, zi = -1;
                 double prod = 1.0;
-                for (int e = e0; e < e1; ++e) {
-                    const uint32_t w = c.edge[e];
-                    double *slot = Lr + (size_t)e * Zc + r;
-                    const double q = __dsub_rn(post((int)(w & 0xff), (int)(w >> 8), e, r), *slot);
+                auto take = [&](int k, double q) {
                     double t = 0.0;
-                    if (q == 0.0) { ++nz; if (zi < 0) zi = e; }
-                    else { t = tanh(q / 2); prod *= t; }
-                    *slot = t;
+                    if (q == 0.0) { ++nz; if (zi < 0) zi = k; }
+                    else { t = bpmath::tanh_half(q); prod *= t; }
+                    slot0[(size_t)k * Zc] = t;
+                };
+                double qx = 0.0;
+                if (nce < ne) {  // LQ = LLR + its one message (:126), Lq = LQ - Lr
+                    const double lr = slot0[(size_t)nce * Zc];
+                    qx = __dsub_rn(chan((c.ncore + i - 4) * Zc + r) + lr, lr);
                 }
-                for (int e = e0; e < e1; ++e) {
-                    double *slot = Lr + (size_t)e * Zc + r;
-                    double out = 0.0;
-                    if (nz == 0) {
-                        const double x = prod / *slot;
-                        out = x >= 1.0 ? 2 * 19.07 : (x <= -1.0 ? -2 * 19.07 : 2 * atanh(x));
-                    } else if (nz == 1 && e == zi) {
-                        out = prod;  // :170 the reference omits 2*atanh here
+                for (int kb = 0; kb < nce; kb += kBpBatch) {
+                    double q[kBpBatch];
+#pragma unroll
+                    for (int u = 0; u < kBpBatch; ++u) {
+                        const int k = kb + u < nce ? kb + u : nce - 1;  // (a repeated load instead of a branch)
+                        const uint32_t w = c.edge[e0 + k];
+                        int v = r + (int)(w >> 8);
+                        if (v >= Zc) v -= Zc;
+                        q[u] = __dsub_rn(LQ[(int)(w & 0xff) * Zc + v], slot0[(size_t)k * Zc]);
                     }
-                    *slot = out;
+#pragma unroll
+                    for (int u = 0; u < kBpBatch; ++u)
+                        if (kb + u < nce) take(kb + u, q[u]);
+                }
+                if (nce < ne) take(nce, qx);
+                for (int kb = 0; kb < ne; kb += kBpBatch) {
+                    double t[kBpBatch];
+#pragma unroll
+                    for (int u = 0; u < kBpBatch; ++u) t[u] = slot0[(size_t)(kb + u < ne ? kb + u : ne - 1) * Zc];
+#pragma unroll
+                    for (int u = 0; u < kBpBatch; ++u) {
+                        const int k = kb + u;
+                        if (k < ne) {
+                            double out = 0.0;
+                            if (nz == 0) {
+                                const double x = prod / t[u];
+                                out = x >= 1.0 ? 2 * 19.07 : (x <= -1.0 ? -2 * 19.07 : bpmath::atanh_twice(x));
+                            } else if (nz == 1 && k == zi) {
+                                out = prod;  // :170 the reference omits 2*atanh here
+                            }
+                            slot0[(size_t)k * Zc] = out;
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -108,6 +138,7 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
             for (int n = tid; n < ncorev; n += kBpThreads) {
                 const int j = n / Zc, v = n - j * Zc;
                 double s = 0.0;
+#pragma unroll 4
                 for (int q = c.colptr[j]; q < c.colptr[j + 1]; ++q) {
                     const uint32_t en = c.centry[q];
                     const int i = en & 63, k = (en >> 6) & 31, back = en >> 16;

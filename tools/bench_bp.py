@@ -9,7 +9,10 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
-from python_5gtoolbox_b200 import engine  # noqa: E402
+from python_5gtoolbox_b200 import _lib, engine  # noqa: E402
+
+if os.environ.get("NRLDPC_SO"):  # kernel experiments: time an alternative build of the library
+    _lib.SO_PATH = os.path.abspath(os.environ["NRLDPC_SO"])
 
 bgn, Zc, L = 1, 384, 10
 K, N, Nf, M = engine.dims(bgn, Zc)
