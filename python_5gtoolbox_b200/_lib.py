@@ -4,7 +4,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libnrldpc_b200.so")
+# NRLDPC_SO=path: kernel experiments load another build of the library (tools/build_variant.sh, same-box A/B runs)
+SO_PATH = os.path.abspath(os.environ["NRLDPC_SO"]) if os.environ.get("NRLDPC_SO") else os.path.join(_HERE, "libnrldpc_b200.so")
 _lib = None
 
 EINVAL, ECUDA, ENOMEM, ENODEV = -1, -2, -3, -4

@@ -69,13 +69,21 @@ NRLDPC_BPM_HD double from_words(int hi, int lo)
     uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; std::memcpy(&x, &u, 8); return x;
 #endif
 }
-// a coarse reciprocal (24 bits) for a correction term
-NRLDPC_BPM_HD double coarse_rcp(double w)
+// single-precision helpers of the exponent estimate in atanh_twice
+NRLDPC_BPM_HD float coarse_rcpf(float d)
 {
 #ifdef __CUDA_ARCH__
-    return (double)__frcp_rn((float)w);
+    return __frcp_rn(d);
 #else
-    return (double)(1.0f / (float)w);
+    return 1.0f / d;
+#endif
+}
+NRLDPC_BPM_HD int float_bits(float v)
+{
+#ifdef __CUDA_ARCH__
+    return __float_as_int(v);
+#else
+    int i; std::memcpy(&i, &v, 4); return i;
 #endif
 }
 
@@ -116,31 +124,31 @@ NRLDPC_BPM_HD double tanh_half(double q)
     return copysign(div_normal(em, em + 2.0), q);
 }
 
-// 2 atanh(x) = log((1 + |x|) / (1 - |x|)), sign of x, for |x| < 1.
-// |x| <= 0.17: the odd series itself.  Above: u = 2|x| / (1 - |x|), w = fl(1 + u) with its rounding error c kept,
-// w = 2^e m with m in [sqrt(1/2), sqrt 2), f = (m - 1) / (m + 1): log w = e ln2 + 2 atanh(f), + c / w.
+// 2 atanh(x) = log w, w = (1 + |x|) / (1 - |x|), sign of x, for |x| < 1.
+// With s = 2^e the power of two nearest to w on the log scale, m = w / s lies in [sqrt(1/2), sqrt 2) and
+// log w = e ln2 + 2 atanh(f), f = (m - 1) / (m + 1) = ((1 + |x|) - s (1 - |x|)) / ((1 + |x|) + s (1 - |x|)):
+// numerator and denominator are one fma each (no rounded intermediate w), one division in all.  Below 1/2, where s is
+// 1 or 2, they are taken as (1 - s) + |x| (1 + s) and (1 + s) + |x| (1 - s), exact in 1 +- s: below 0.17 e = 0 and
+// f = |x| exactly; from 1/2 up 1 - |x| is exact and the form above is used as it stands.  e only has to be roughly right (it moves f inside the series' range), so it
+// comes from a single-precision estimate of w.
 NRLDPC_BPM_HD double atanh_twice(double x)
 {
     const double a = fabs(x);
-    const bool small = a <= 0.17;
-    const double u = div_normal(a + a, 1.0 - a);
-    const double w = 1.0 + u;
-    const double c = u - (w - 1.0);
-    int hi = hi_word(w);
-    int e = (hi >> 20) - 1023;
-    hi = (hi & 0x000fffff) | 0x3ff00000;
-    if (hi >= 0x3ff6a09f) { hi -= 0x00100000; ++e; }  // m >= sqrt 2 (to 20 bits) -> m / 2
-    const double m = from_words(hi, lo_word(w));
-    double f = div_normal(m - 1.0, m + 1.0);
-    double corr = c * coarse_rcp(w);
-    if (small) { f = a; e = 0; corr = 0.0; }
-    const double s = f * f;
+    const float wf = (float)(1.0 + a) * coarse_rcpf((float)(1.0 - a)) * 1.41421356f;  // >= 1.41, < 2^56
+    const int e = (float_bits(wf) >> 23) - 127;                                       // floor(log2 w + 1/2)
+    const double s = from_words((1023 + e) << 20, 0);
+    const double c = 1.0 + a, d = 1.0 - a;
+    const bool upper = a >= 0.5;
+    const double num = upper ? fma(-s, d, c) : fma(a, 1.0 + s, 1.0 - s);
+    const double den = upper ? fma(s, d, c) : fma(a, 1.0 - s, 1.0 + s);
+    const double f = div_normal(num, den);
+    const double g = f * f;
     double p = NRLDPC_BPM_C(12);
 #pragma unroll
-    for (int i = 13; i < 22; ++i) p = fma(p, s, NRLDPC_BPM_C(i));
+    for (int i = 13; i < 22; ++i) p = fma(p, g, NRLDPC_BPM_C(i));
     const double ed = (double)e;
     const double f2 = f + f;
-    double r = fma(f2 * s, p, fma(ed, kLn2Lo, corr));  // the small terms first
+    double r = fma(f2 * g, p, ed * kLn2Lo);  // the small terms first
     r += f2;
     r = fma(ed, kLn2Hi, r);
     return copysign(r, x);

@@ -8,7 +8,7 @@
 //   per row:  t_e = tanh(Lq_e / 2), P = prod t_e, Lr_e = 2 atanh(P / t_e) clipped to +-38.14 when |x| >= 1 (:158-163);
 //             exactly one zero input: that edge gets prod tanh(others) WITHOUT the 2 atanh (:164-170); >= 2 zeros: 0.
 // Per-edge messages are needed (no min1/min2 compression for BP): Lr[nnz][Zc] doubles = 970 KB per codeblock at BG1
-// Zc=384 lives in a per-CTA global workspace that stays in L2 (persistent CTAs), the posteriors of the core columns in
+// Zc=384 lives in a per-CTA global workspace (persistent CTAs; 287 MB in all, so half of it comes from HBM), the posteriors of the core columns in
 // shared memory, the degree-1 extension variables are recomputed from their single message.  The circulant shift is
 // index arithmetic on the lifted index, the tables sit in the constant bank (QcCfg by value).
 #include <algorithm>
@@ -19,7 +19,10 @@
 namespace nrldpc {
 namespace {
 
-constexpr int kBpThreads = 512;
+#ifndef NRLDPC_BP_THREADS
+#define NRLDPC_BP_THREADS 512
+#endif
+constexpr int kBpThreads = NRLDPC_BP_THREADS;  // 1024 / kBpThreads persistent CTAs per SM
 constexpr int kBpBatch = 4;  // edges of a row whose workspace words are in flight together
 
 template <typename TIn>
@@ -27,11 +30,18 @@ __global__ void __launch_bounds__(kBpThreads)
 bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B, int max_iter, int early_term,
              double *__restrict__ work, int8_t *__restrict__ ck, uint8_t *__restrict__ status, int32_t *__restrict__ iters)
 {
-    extern __shared__ double LQ[];  // [ncore][Zc]
+    extern __shared__ double LQ[];  // [ncore][Zc], then (Zc a multiple of 32) the packed hard decisions: uint32 [Nfull / 32]
     __shared__ int s_any;
     const int Zc = c.Zc, tid = threadIdx.x, nnz = c.rowptr[c.nrows];
     double *Lr = work + (size_t)blockIdx.x * (size_t)nnz * Zc;  // [edge][r]
     const int nchk = c.nrows * Zc, ncorev = c.ncore * Zc;
+    // In-loop syndrome (:107-114) on bit-packed decisions when Zc is a multiple of 32: whoever computes a posterior (the
+    // variable pass; sweep 2 of a check row for its degree-1 extension variable) ballots its sign into hard[n / 32], a warp
+    // always holds 32 consecutive lifted indices of one block; the syndrome word of (row-block, word) is then the XOR of
+    // funnel-shifted words, 32 checks per lane, instead of one walk over the edges per check.
+    const bool packed = (Zc & 31) == 0;
+    const int W = Zc >> 5;
+    uint32_t *hard = reinterpret_cast<uint32_t *>(LQ + ncorev);
 
     for (int cb = blockIdx.x; cb < B; cb += gridDim.x) {
         const TIn *L0 = llr + (size_t)cb * c.N;
@@ -39,6 +49,11 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
         auto chan = [&](int n) -> double { return n < 2 * Zc ? 0.0 : (double)L0[n - 2 * Zc] + 0.0; };
         // :94-101  LQ = LLRin, Lr = 0
         for (int n = tid; n < ncorev; n += kBpThreads) LQ[n] = chan(n);
+        if (packed)
+            for (int n = tid; n < c.Nfull; n += kBpThreads) {  // Lr = 0: every posterior is its channel LLR
+                const uint32_t b = __ballot_sync(0xffffffffu, chan(n) < 0.0);
+                if ((tid & 31) == 0) hard[n >> 5] = b;
+            }
         for (int e = tid; e < nnz * Zc; e += kBpThreads) Lr[e] = 0.0;
         if (tid == 0) s_any = 0;
         __syncthreads();
@@ -50,7 +65,7 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
                 if (v >= Zc) v -= Zc;
                 return LQ[j * Zc + v];
             }
-            return chan(j * Zc + r) + Lr[(size_t)e * Zc + r];  // degree-1 extension variable: LQ = LLR + its one message (:126)
+            return chan(j * Zc + r) + Lr[e * Zc + r];  // degree-1 extension variable: LQ = LLR + its one message (:126)
         };
         auto syndrome = [&](bool final_rule) -> int {
             int any = 0;
@@ -67,11 +82,30 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
             return any;
         };
 
+        auto syndrome_packed = [&]() -> int {
+            uint32_t any = 0;
+            for (int t = tid; t < c.nrows * W; t += kBpThreads) {
+                const int i = t / W, w = t - i * W;
+                uint32_t acc = i >= 4 ? hard[(c.ncore + i - 4) * W + w] : 0u;
+                for (int e = c.rowptr[i]; e < c.rowptr[i + 1] - (i >= 4); ++e) {
+                    const uint32_t ew = c.edge[e];
+                    const int P = (int)(ew >> 8);
+                    int w0 = w + (P >> 5);  // check 32 w + b reads variable 32 w + b + P (mod Zc)
+                    if (w0 >= W) w0 -= W;
+                    const int w1 = w0 + 1 < W ? w0 + 1 : 0;
+                    const uint32_t *col = hard + (int)(ew & 0xff) * W;
+                    acc ^= __funnelshift_r(col[w0], col[w1], P & 31);
+                }
+                any |= acc;
+            }
+            return any != 0;
+        };
+
         bool done = false;
         int it = 0;
         for (; it < max_iter; ++it) {
-            // :107-114 syndrome of the decisions LQ < 0
-            if (syndrome(false)) s_any = 1;
+            // :107-114 syndrome of the decisions LQ < 0 (its only use is the early exit)
+            if (early_term && (packed ? syndrome_packed() : syndrome(false))) s_any = 1;
             __syncthreads();
             const int bad = s_any;
             __syncthreads();
@@ -84,19 +118,20 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
             for (int m = tid; m < nchk; m += kBpThreads) {
                 const int i = m / Zc, r = m - i * Zc;
                 const int e0 = c.rowptr[i], ne = c.rowptr[i + 1] - e0, nce = ne - (i >= 4);
-                double *slot0 = Lr + (size_t)e0 * Zc + r;  // edge k of the row: slot0[k * Zc]
+                double *slot0 = Lr + (e0 * Zc + r);  // edge k of the row: slot0[k * Zc] (32-bit offsets: nnz Zc < 2^17)
                 int nz = 0, zi = -1;
                 double prod = 1.0;
                 auto take = [&](int k, double q) {
                     double t = 0.0;
                     if (q == 0.0) { ++nz; if (zi < 0) zi = k; }
                     else { t = bpmath::tanh_half(q); prod *= t; }
-                    slot0[(size_t)k * Zc] = t;
+                    slot0[k * Zc] = t;
                 };
-                double qx = 0.0;
+                double qx = 0.0, chx = 0.0;
                 if (nce < ne) {  // LQ = LLR + its one message (:126), Lq = LQ - Lr
-                    const double lr = slot0[(size_t)nce * Zc];
-                    qx = __dsub_rn(chan((c.ncore + i - 4) * Zc + r) + lr, lr);
+                    const double lr = slot0[nce * Zc];
+                    chx = chan((c.ncore + i - 4) * Zc + r);
+                    qx = __dsub_rn(chx + lr, lr);
                 }
                 for (int kb = 0; kb < nce; kb += kBpBatch) {
                     double q[kBpBatch];
@@ -106,17 +141,18 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
                         const uint32_t w = c.edge[e0 + k];
                         int v = r + (int)(w >> 8);
                         if (v >= Zc) v -= Zc;
-                        q[u] = __dsub_rn(LQ[(int)(w & 0xff) * Zc + v], slot0[(size_t)k * Zc]);
+                        q[u] = __dsub_rn(LQ[(int)(w & 0xff) * Zc + v], slot0[k * Zc]);
                     }
 #pragma unroll
                     for (int u = 0; u < kBpBatch; ++u)
                         if (kb + u < nce) take(kb + u, q[u]);
                 }
                 if (nce < ne) take(nce, qx);
+                double last = 0.0;  // the new message on the row's last edge
                 for (int kb = 0; kb < ne; kb += kBpBatch) {
                     double t[kBpBatch];
 #pragma unroll
-                    for (int u = 0; u < kBpBatch; ++u) t[u] = slot0[(size_t)(kb + u < ne ? kb + u : ne - 1) * Zc];
+                    for (int u = 0; u < kBpBatch; ++u) t[u] = slot0[(kb + u < ne ? kb + u : ne - 1) * Zc];
 #pragma unroll
                     for (int u = 0; u < kBpBatch; ++u) {
                         const int k = kb + u;
@@ -128,9 +164,14 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
                             } else if (nz == 1 && k == zi) {
                                 out = prod;  // :170 the reference omits 2*atanh here
                             }
-                            slot0[(size_t)k * Zc] = out;
+                            slot0[k * Zc] = out;
+                            last = out;
                         }
                     }
+                }
+                if (packed && early_term && nce < ne) {  // (warp-uniform: 32 consecutive checks of one row-block)
+                    const uint32_t b = __ballot_sync(0xffffffffu, chx + last < 0.0);
+                    if ((tid & 31) == 0) hard[((c.ncore + i - 4) * Zc + r) >> 5] = b;
                 }
             }
             __syncthreads();
@@ -144,9 +185,14 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
                     const int i = en & 63, k = (en >> 6) & 31, back = en >> 16;
                     int r = v + back;
                     if (r >= Zc) r -= Zc;
-                    s = __dadd_rn(s, Lr[(size_t)(c.rowptr[i] + k) * Zc + r]);
+                    s = __dadd_rn(s, Lr[(c.rowptr[i] + k) * Zc + r]);
                 }
-                LQ[n] = __dadd_rn(chan(n), s);
+                const double x = __dadd_rn(chan(n), s);
+                LQ[n] = x;
+                if (packed) {
+                    const uint32_t b = __ballot_sync(0xffffffffu, x < 0.0);
+                    if ((tid & 31) == 0) hard[n >> 5] = b;
+                }
             }
             __syncthreads();
         }
@@ -163,7 +209,7 @@ bp_qc_kernel(const __grid_constant__ QcCfg c, const TIn *__restrict__ llr, int B
             if (n < ncorev) x = LQ[n];
             else {
                 const int i = 4 + (n - ncorev) / Zc, r = (n - ncorev) % Zc;
-                x = chan(n) + Lr[(size_t)(c.rowptr[i + 1] - 1) * Zc + r];
+                x = chan(n) + Lr[(c.rowptr[i + 1] - 1) * Zc + r];
             }
             out[n] = (int8_t)(done ? (x < 0.0) : (x <= 0.0));
         }
@@ -181,11 +227,12 @@ int launch_bp_qc(const QcCfg &c, const void *d_llr, int is_f64, int B, int max_i
                  uint8_t *d_status, int32_t *d_iters, cudaStream_t s)
 {
     if (B <= 0) return NRLDPC_OK;
-    const int nnz = c.rowptr[c.nrows], smem = c.ncore * c.Zc * (int)sizeof(double);
+    const int nnz = c.rowptr[c.nrows];
+    const int smem = c.ncore * c.Zc * (int)sizeof(double) + (c.Zc % 32 == 0 ? c.Nfull / 32 * 4 : 0);  // posteriors + packed decisions
     int dev = 0, sms = 148;
     NRLDPC_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = std::min(B, 2 * sms);  // two CTAs per SM (80 KB of shared memory each at Zc = 384)
+    const int grid = std::min(B, (1024 / kBpThreads) * sms);  // two CTAs per SM (83 KB of shared memory each at Zc = 384)
     ScratchBuf work;
     NRLDPC_CUDA(work.alloc((size_t)grid * nnz * c.Zc * sizeof(double), s));
     if (is_f64) {

@@ -32,6 +32,14 @@ int main() {
         if (e > worst_a) { worst_a = e; wa_at = x; }
         el = ulp_err(2*atanh(x), 2 * atanhl((long double)x)); if (el > worst_la) worst_la = el;
     }
+    // the ends of the domain: the largest double below 1, tiny arguments (the series' first term alone)
+    const double top = nextafter(1.0, 0.0), tops[4] = {top, -top, 1e-300, -3e-9};
+    for (double x : tops) {
+        double e = ulp_err(atanh_twice(x), 2 * atanhl((long double)x));
+        if (e > worst_a) { worst_a = e; wa_at = x; }
+        e = ulp_err(tanh_half(x), tanhl((long double)x / 2));
+        if (e > worst_t) { worst_t = e; wt_at = x; }
+    }
     printf("tanh_half max ulp %.3f at %.17g (libm %.3f)\natanh_twice max ulp %.3f at %.17g (libm %.3f)\n", worst_t, wt_at, worst_lt, worst_a, wa_at, worst_la);
     printf("%.17g %.17g %.17g\n", tanh_half(0.0), tanh_half(1e300), atanh_twice(0.0));
     return 0;

@@ -1,9 +1,10 @@
 #!/bin/bash
-# A/B of the sum-product kernel against a saved build (build/variants/libnrldpc_old.so) + its tests + an ncu capture
+# A/B of the sum-product kernel against saved builds (build/variants/libnrldpc_*.so) + its tests + an ncu capture
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-V=$PWD/build/variants/libnrldpc_old.so
-[ -f "$V" ] && { echo "== old"; NRLDPC_SO=$V python tools/bench_bp.py 2>&1 | tail -2; }
+for V in build/variants/libnrldpc_*.so; do
+  [ -f "$V" ] && { echo "== $V"; NRLDPC_SO=$PWD/$V python tools/bench_bp.py 2>&1 | tail -2; }
+done
 echo "== shipped"; python tools/bench_bp.py 2>&1 | tee gpurun_out/r2_bp_bench.log | tail -2
 timeout 900 python -m pytest tests -m gpu -x -q -k "bp" 2>&1 | tail -3
 python tools/profile_bp.py 2>&1 | tail -1
