@@ -401,7 +401,7 @@ def host_link_ceiling(torch, dev, h_llr, barrier, world, dist):
 
 
 def other_kernel_lines(torch, engine, dev, hbm_peak):
-    """Encoder and bit-flipping lines (SURVEY 8(d) byte conventions), CUDA events, batches larger than L2."""
+    """Encoder, bit-flipping and sum-product lines (SURVEY 8(d) byte conventions), CUDA events, batches larger than L2."""
     out = []
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 
@@ -441,6 +441,12 @@ def other_kernel_lines(torch, engine, dev, hbm_peak):
     nbytes = B * (4 * N + Nf)
     out.append({"kernel": f"bit-flipping BG{bgn} Zc={Zc} L={L} (nothing converges at +1 dB)", "codeblocks": B, "ms": ms,
                 "info_gbit_per_s": B * K / ms / 1e6, "bytes_8d": nbytes, "gb_per_s": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / hbm_peak})
+    # sum-product (algo='BP', float64 like the reference): issue- and latency-bound, profiles/r2_bp_ncu_summary.md
+    Bp, Lp = 1 << 12, 10
+    ms = timed(lambda: engine.decode_bp_batch(llr[:Bp], Zc, bgn, Lp), reps=2)
+    nbytes = Bp * (4 * N + Nf)
+    out.append({"kernel": f"sum-product BG{bgn} Zc={Zc} L={Lp} (early termination, +1 dB)", "codeblocks": Bp, "ms": ms,
+                "info_gbit_per_s": Bp * K / ms / 1e6, "bytes_8d": nbytes, "gb_per_s": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / hbm_peak})
     return out
 
 
