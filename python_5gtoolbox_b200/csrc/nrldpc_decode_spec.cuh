@@ -37,7 +37,10 @@ namespace nrldpc {
 
 namespace {
 
-constexpr int kMaxS = 16;  // warp groups per r-tile
+#ifndef NRLDPC_MAX_S
+#define NRLDPC_MAX_S 16
+#endif
+constexpr int kMaxS = 16;  // warp groups per r-tile (array bound)
 #ifndef NRLDPC_MULTI_CTA_BELOW
 #define NRLDPC_MULTI_CTA_BELOW 144  // (176 measured: BG1 Zc=160 785 vs 826, Zc=144 712 vs 745 G edge-iterations/s -- one CTA of 30 warps wins there)
 #endif
@@ -184,7 +187,12 @@ template <int BGN, int ZC_, bool RR_ = false> struct Code {
                                          : ((NRLDPC_TWO_CTAS && 2 * (smem_bytes + 1024) <= 228 * 1024 && 16 / tiles >= 1) ? 2 : 1);
     static constexpr int Smax0 = (32 / ctas) / tiles;
     static constexpr int Smax = Smax0 < 1 ? 1 : Smax0;
-    static constexpr int S = Smax < kMaxS ? Smax : kMaxS, nwarps = tiles * S;
+    // At most 3 warp groups from Zc = 144 up (4 with 7 r-tiles).  Measured on Zc = 144 ... 256 (profiles/r2_zc_groups_ab.md):
+    // an iteration takes ~9 us whatever the lifting size and whether 12 or 30 warps run it -- ncu shows the warps waiting
+    // for instructions (no_instruction 8-11 per issue at Zc = 176 / 144 against 0.4 at Zc = 384), every group streams
+    // its own straight-line code -- so more groups buy nothing, and 3 x tiles warps keep > 64 registers per thread.
+    static constexpr int Scap = (ZC >= kMultiCtaBelow && NRLDPC_MAX_S > 3) ? (tiles == 7 ? 4 : 3) : NRLDPC_MAX_S;
+    static constexpr int S = Smax < Scap ? Smax : Scap, nwarps = tiles * S;
     static constexpr int lq_base(int j) { return off_lq + j * LQS * 4; }
     static constexpr int mags_base(int i) { return off_mags + i * LQS * 4; }  // mag1 of check 0; mag2 sits mag2_dist further
     static constexpr int bits_base(int i)  // the word of check r sits at bits_base(i) + 4 r
