@@ -191,7 +191,21 @@ template <int BGN, int ZC_, bool RR_ = false> struct Code {
     // an iteration takes ~9 us whatever the lifting size and whether 12 or 30 warps run it -- ncu shows the warps waiting
     // for instructions (no_instruction 8-11 per issue at Zc = 176 / 144 against 0.4 at Zc = 384), every group streams
     // its own straight-line code -- so more groups buy nothing, and 3 x tiles warps keep > 64 registers per thread.
-    static constexpr int Scap = (ZC >= kMultiCtaBelow && NRLDPC_MAX_S > 3) ? (tiles == 7 ? 4 : 3) : NRLDPC_MAX_S;
+    // Below 144 (several CTAs per SM) the best group count is irregular and depends on the operating point: one group per
+    // CTA is 20-27 % faster at BG1 Zc = 56 / 60 / 64 when nothing converges (-3 dB, 10 iterations), 40 % slower at
+    // 44 / 52 / 112, and 4-9 % SLOWER at the same 56 / 60 / 64 at +1 dB, where codeblocks leave after ~7 iterations and
+    // the fewer warps pay at the codeblock boundaries.  Only the BG2 sizes that win at both points carry a count here
+    // (profiles/r2_zc_groups_ab.md, same box).  -DNRLDPC_MAX_S=n (n <= 3) overrides, -DNRLDPC_GROUP_TABLE=0 disables.
+    static constexpr int small_groups()
+    {
+        if (BGN == 2 && (ZC == 44 || ZC == 72 || ZC == 88 || ZC == 96 || ZC == 120 || ZC == 128)) return 1;
+        return NRLDPC_MAX_S;
+    }
+#ifndef NRLDPC_GROUP_TABLE
+#define NRLDPC_GROUP_TABLE 1  // 0: as many groups as 32 warps per SM allow (the layout before the measurements above)
+#endif
+    static constexpr int Scap = (NRLDPC_MAX_S <= 3 || !NRLDPC_GROUP_TABLE) ? NRLDPC_MAX_S
+                              : (ZC >= kMultiCtaBelow ? (tiles == 7 ? 4 : 3) : small_groups());
     static constexpr int S = Smax < Scap ? Smax : Scap, nwarps = tiles * S;
     static constexpr int lq_base(int j) { return off_lq + j * LQS * 4; }
     static constexpr int mags_base(int i) { return off_mags + i * LQS * 4; }  // mag1 of check 0; mag2 sits mag2_dist further
