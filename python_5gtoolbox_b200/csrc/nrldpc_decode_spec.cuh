@@ -187,7 +187,8 @@ template <int BGN, int ZC_, bool RR_ = false> struct Code {
                                          : ((NRLDPC_TWO_CTAS && 2 * (smem_bytes + 1024) <= 228 * 1024 && 16 / tiles >= 1) ? 2 : 1);
     static constexpr int Smax0 = (32 / ctas) / tiles;
     static constexpr int Smax = Smax0 < 1 ? 1 : Smax0;
-    // At most 3 warp groups from Zc = 144 up (4 with 7 r-tiles).  Measured on Zc = 144 ... 256 (profiles/r2_zc_groups_ab.md):
+    // At most 3 warp groups from Zc = 144 up (4 with 7 r-tiles; 2 at Zc = 320, whose 3 x 10 warps would cap the registers at 64:
+    // +6.5-7 % with fixed iterations, +9-14 % with early termination at an operating point, both base graphs).  Measured on Zc = 144 ... 256 (profiles/r2_zc_groups_ab.md):
     // an iteration takes ~9 us whatever the lifting size and whether 12 or 30 warps run it -- ncu shows the warps waiting
     // for instructions (no_instruction 8-11 per issue at Zc = 176 / 144 against 0.4 at Zc = 384), every group streams
     // its own straight-line code -- so more groups buy nothing, and 3 x tiles warps keep > 64 registers per thread.
@@ -205,7 +206,7 @@ template <int BGN, int ZC_, bool RR_ = false> struct Code {
 #define NRLDPC_GROUP_TABLE 1  // 0: as many groups as 32 warps per SM allow (the layout before the measurements above)
 #endif
     static constexpr int Scap = (NRLDPC_MAX_S <= 3 || !NRLDPC_GROUP_TABLE) ? NRLDPC_MAX_S
-                              : (ZC >= kMultiCtaBelow ? (tiles == 7 ? 4 : 3) : small_groups());
+                              : (ZC >= kMultiCtaBelow ? (tiles == 7 ? 4 : (tiles == 10 ? 2 : 3)) : small_groups());
     static constexpr int S = Smax < Scap ? Smax : Scap, nwarps = tiles * S;
     static constexpr int lq_base(int j) { return off_lq + j * LQS * 4; }
     static constexpr int mags_base(int i) { return off_mags + i * LQS * 4; }  // mag1 of check 0; mag2 sits mag2_dist further
